@@ -1,0 +1,18 @@
+"""gpdoemd_b200 -- B200-native design-evaluation hot path of GPdoemd.
+
+GP predictive mean/variance and p-derivatives -> Taylor marginals -> design criteria -> argmax, in
+FP64 CUDA for sm_100a behind the reference's Python classes and function signatures.  Importing this
+package does not need a GPU; the first call that computes anything does, and raises if the CUDA library
+or device is missing (there is no CPU fallback).
+"""
+from . import design_criteria, kernels, marginal, scoring
+from .context import Context, get_context
+from .design_criteria import AW, BF, BH, HR, JR
+from .gp_state import ExactGP, GPState
+from .marginal import taylor_first_order, taylor_second_order
+from .models import GPModel
+from .scoring import ShardedScorer, score_designs, score_designs_dev
+
+__all__ = ['GPModel', 'GPState', 'ExactGP', 'Context', 'get_context', 'kernels', 'marginal', 'design_criteria',
+           'scoring', 'taylor_first_order', 'taylor_second_order', 'HR', 'BH', 'BF', 'AW', 'JR', 'score_designs',
+           'score_designs_dev', 'ShardedScorer']

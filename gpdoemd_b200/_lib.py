@@ -1,0 +1,125 @@
+"""ctypes binding of libgpdoemd_b200.so (include/gpdoemd_b200.h).
+
+There is no CPU fallback: if the shared library is missing or no B200 is visible, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libgpdoemd_b200.so')
+
+KERNEL_IDS = {'RBF': 0, 'Exponential': 1, 'Matern32': 2, 'Matern52': 3, 'Cosine': 4, 'RatQuad': 5}
+CRITERION_IDS = {'HR': 0, 'BH': 1, 'BF': 2, 'AW': 3, 'JR': 4}
+FAMILIES = ('eval', 'tri', 'gram', 'marginal', 'criteria', 'argmax', 'setup')
+NFAMILIES = len(FAMILIES)
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+c_void_pp = C.POINTER(C.c_void_p)
+
+
+class GpDesc(C.Structure):
+    _fields_ = [('kernel', C.c_int32), ('n', C.c_int32), ('dim_x', C.c_int32), ('dim_p', C.c_int32),
+                ('n_x_active', C.c_int32), ('x_active', c_int32_p), ('var_x', C.c_double), ('ls_x', c_double_p),
+                ('power_x', C.c_double), ('var_p', C.c_double), ('ls_p', c_double_p), ('power_p', C.c_double),
+                ('Z', c_double_p), ('alpha', c_double_p), ('L', c_double_p)]
+
+
+class GpdError(RuntimeError):
+    pass
+
+
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    'gpd_create': (C.c_int, [C.c_int, c_void_pp]),
+    'gpd_destroy': (None, [C.c_void_p]),
+    'gpd_last_error': (C.c_char_p, []),
+    'gpd_set_scratch_bytes': (C.c_int, [C.c_void_p, C.c_uint64]),
+    'gpd_set_option': (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    'gpd_launch_count': (C.c_uint64, [C.c_void_p]),
+    'gpd_profile_enable': (C.c_int, [C.c_void_p, C.c_int]),
+    'gpd_profile_read': (C.c_int, [C.c_void_p, c_double_p, C.POINTER(C.c_uint64), c_double_p]),
+    'gpd_timer_start': (C.c_int, [C.c_void_p]),
+    'gpd_timer_stop': (C.c_int, [C.c_void_p, c_double_p]),
+    'gpd_sync': (C.c_int, [C.c_void_p]),
+    'gpd_probe_fp64_peak': (C.c_int, [C.c_void_p, c_double_p]),
+    'gpd_flush_l2': (C.c_int, [C.c_void_p]),
+    'gpd_gp_upload': (C.c_int, [C.c_void_p, C.POINTER(GpDesc), c_void_pp]),
+    'gpd_gp_free': (None, [C.c_void_p]),
+    'gpd_model_create': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_int32_p, c_void_pp,
+                                   c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_void_pp]),
+    'gpd_model_free': (None, [C.c_void_p]),
+    'gpd_model_set_pmean_sigma': (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
+    'gpd_model_set_pstar': (C.c_int, [C.c_void_p, c_double_p]),
+    'gpd_predict': (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_double_p]),
+    'gpd_dmu_dp': (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_double_p]),
+    'gpd_d2mu_dp2': (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_double_p]),
+    'gpd_ds2_dp': (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_double_p]),
+    'gpd_d2s2_dp2': (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_double_p]),
+    'gpd_hooks': (C.c_int, [C.c_void_p, c_double_p, C.c_int64, C.c_int32] + [c_double_p] * 6),
+    'gpd_marginal': (C.c_int, [C.c_void_p, c_double_p, C.c_int64, C.c_int, c_double_p, c_double_p]),
+    'gpd_marginal_assemble': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int32] + [c_double_p] * 7),
+    'gpd_criterion': (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, C.c_int64, C.c_int32, C.c_int32,
+                                c_double_p, c_double_p, c_double_p]),
+    'gpd_argmax': (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_double_p, C.POINTER(C.c_int64)]),
+    'gpd_score': (C.c_int, [C.c_void_p, c_void_pp, C.c_int32, c_double_p, C.c_int64, C.c_int, C.c_int, c_double_p,
+                            c_double_p, c_double_p, c_double_p, C.POINTER(C.c_int64), C.c_int64]),
+    'gpd_score_dev': (C.c_int, [C.c_void_p, c_void_pp, C.c_int32, C.c_void_p, C.c_int64, C.c_int, C.c_int, c_double_p,
+                                c_double_p, C.c_void_p, c_double_p, C.POINTER(C.c_int64), C.c_int64]),
+    'gpd_dev_alloc': (C.c_int, [C.c_void_p, C.c_uint64, c_void_pp]),
+    'gpd_dev_free': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'gpd_dev_upload': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    'gpd_dev_download': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    'gpd_host_alloc_pinned': (C.c_int, [C.c_void_p, C.c_uint64, c_void_pp]),
+    'gpd_host_free_pinned': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'gpd_dev_fill_uniform': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_int64,
+                                       c_double_p, c_double_p]),
+    'gpd_layout_a_index': (C.c_int32, [C.c_int32] * 3),
+    'gpd_layout_a_row': (C.c_int32, [C.c_int32] * 2),
+    'gpd_layout_a_col': (C.c_int32, [C.c_int32] * 2),
+    'gpd_layout_b_index': (C.c_int32, [C.c_int32] * 2),
+    'gpd_layout_tile_offset': (C.c_int64, [C.c_int32] * 4),
+    'gpd_binary_combo_weight': (C.c_int32, [C.c_int32] * 2),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library and declare every prototype of include/gpdoemd_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GpdError('%s is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                       '(or `make -C gpdoemd_b200/csrc`); there is no CPU fallback' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header and library out of sync
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def check(rc):
+    if rc != 0:
+        raise GpdError(load().gpd_last_error().decode('utf-8', 'replace'))
+
+
+def dptr(a):
+    """float64 C-contiguous array -> double* (None -> NULL)."""
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags['C_CONTIGUOUS']
+    return a.ctypes.data_as(c_double_p)
+
+
+def as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)

@@ -1,0 +1,1288 @@
+// Host side of libgpdoemd_b200.so: the C ABI of include/gpdoemd_b200.h on top of the kernels.
+//
+// Every entry point mirrors one reference interface (file:line in the header).  Nothing is computed on
+// the CPU here: the host code only plans chunks, builds descriptor tables and launches kernels.
+//
+// Data flow of one candidate chunk (Nc candidates, all on ctx->stream):
+//   route (binary combos) -> eval (kx rows, kx.C contractions, RHS panels) -> tri (V = L^-1 R on DMMA,
+//   ||v||^2) [-> gram, tri backward (beta), beta contraction for the variance derivatives]
+//   -> finalize (original units) [-> assemble (Taylor marginal) -> criterion -> argmax]
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/gpdoemd_b200.h"
+#include "common.cuh"
+
+namespace gpd {
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) GPD_CUDA(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        GPD_CUDA(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+enum Family { F_EVAL = 0, F_TRI = 1, F_GRAM = 2, F_MARG = 3, F_CRIT = 4, F_ARGMAX = 5, F_SETUP = 6 };
+}  // namespace gpd
+
+using namespace gpd;
+
+struct gpd_ctx {
+    int device = 0, num_sms = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t scratch_limit = 6ull << 30;
+    DevBuf scratch, tables, flush;
+    uint64_t launches = 0;
+    int tri_variant = 0;
+    // profiling: event pairs recorded without synchronising, resolved in gpd_profile_read
+    int profile = 0;
+    struct Span { cudaEvent_t a, b; int fam; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> pool;
+    double fam_ms[GPD_NFAMILIES] = {0}, fam_flops[GPD_NFAMILIES] = {0};
+    uint64_t fam_launches[GPD_NFAMILIES] = {0};
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    double* best_val_dev = nullptr;
+    long long* best_idx_dev = nullptr;
+    void* argmax_partial = nullptr;
+};
+
+struct gpd_gp {
+    gpd_ctx* ctx = nullptr;
+    int kernel = 0, n = 0, n_pad = 0, nblk = 0, D = 0, P = 0, nx = 0;
+    int x_active[kMaxXDims];
+    double ls_x[kMaxXDims];
+    double var_x = 1, var_p = 1, power_x = 2, power_p = 2;
+    double *Xs = nullptr, *Zp = nullptr, *alpha = nullptr, *ls_p = nullptr;
+    double *C = nullptr, *G = nullptr, *H = nullptr;
+    double *LinvF = nullptr, *LinvB = nullptr;
+};
+
+struct gpd_model {
+    gpd_ctx* ctx = nullptr;
+    int E = 0, D = 0, P = 0, nb = 0, R = 1;
+    int binary[kMaxBinary];
+    std::vector<gpd_gp*> gps;  // E * R
+    std::vector<double> xmin, xmax, pmin, pmax, ymean, ystd, pmean, Sigma;
+    bool has_pmean = false, has_sigma = false;
+    ModelXform* xf_dev = nullptr;      // [0] real unit conversions, [1] identity (transformed-unit hooks)
+    double* pstar_dev = nullptr;
+    std::vector<double> pstar;         // p* currently folded into the GPs' C/G/H tables
+    int *bcols_dev = nullptr, *weights_dev = nullptr;
+};
+
+namespace gpd {
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Span {
+    gpd_ctx* c;
+    int fam;
+    cudaEvent_t a = nullptr, b = nullptr;
+    Span(gpd_ctx* ctx, int family, uint64_t nlaunch, double flops) : c(ctx), fam(family) {
+        c->launches += nlaunch;
+        if (!c->profile) return;
+        c->fam_launches[fam] += nlaunch;
+        c->fam_flops[fam] += flops;
+        a = take();
+        b = take();
+        cudaEventRecord(a, c->stream);
+    }
+    ~Span() {
+        if (!a) return;
+        cudaEventRecord(b, c->stream);
+        c->spans.push_back({a, b, fam});
+    }
+    cudaEvent_t take() {
+        cudaEvent_t e;
+        if (!c->pool.empty()) {
+            e = c->pool.back();
+            c->pool.pop_back();
+        } else {
+            cudaEventCreate(&e);
+        }
+        return e;
+    }
+};
+
+static int resolve_spans(gpd_ctx* c) {
+    if (c->spans.empty()) return 0;
+    GPD_CUDA(cudaStreamSynchronize(c->stream));
+    for (auto& s : c->spans) {
+        float ms = 0.f;
+        GPD_CUDA(cudaEventElapsedTime(&ms, s.a, s.b));
+        c->fam_ms[s.fam] += ms;
+        c->pool.push_back(s.a);
+        c->pool.push_back(s.b);
+    }
+    c->spans.clear();
+    return 0;
+}
+
+// bump allocator over the context scratch region
+struct Bump {
+    char* base;
+    size_t off = 0, cap;
+    Bump(void* p, size_t c) : base((char*)p), cap(c) {}
+    template <typename T>
+    T* take(size_t count) {
+        off = align_up(off, 256);
+        T* r = (T*)(base + off);
+        off += count * sizeof(T);
+        return r;
+    }
+};
+
+// ---- per-call plan ---------------------------------------------------------------------------
+enum HookFlags { WANT_DMU = 1, WANT_D2MU = 2, WANT_DS2 = 4, WANT_D2S2 = 8 };
+
+struct GpEntry {
+    gpd_gp* gp;
+    int model, e, r;
+    long long panel_off;
+};
+struct Group {          // GPs evaluated by one eval launch: same kernel class, active dims count and P
+    int kernel, nx, P;
+    std::vector<int> entries;
+    int item_begin = 0, item_count = 0;
+};
+struct ModelBufs {
+    RawOut raw;
+    int ldraw = 0, ng = 0, ldmu = 0;
+    double *mu = nullptr, *s2 = nullptr, *dmu = nullptr, *d2mu = nullptr, *ds2 = nullptr, *d2s2 = nullptr;
+    int* idx = nullptr;
+    int* counts = nullptr;
+};
+struct Plan {
+    std::vector<gpd_model*> models;
+    int flags = 0;
+    bool transformed = false;       // X, outputs in the reference's transformed units (the `_`-hooks)
+    bool need_W = false;            // variance derivatives: 1+P right-hand sides, V panels kept
+    int chunk = 0, tiles = 0;
+    std::vector<GpEntry> entries;
+    std::vector<Group> groups;
+    std::vector<ModelBufs> mb;
+    size_t per_cand_bytes = 0;      // scratch bytes per candidate (panels + raws + hook outputs)
+    long long panel_unit = 0;       // sum over GPs of n_pad (doubles per candidate per RHS kind)
+    int max_nrhs = 1;
+    // device tables
+    GpView* views_dev = nullptr;
+    Item* items_dev = nullptr;
+    RawOut* raws_dev = nullptr;
+    double *panels_in = nullptr, *panels_out = nullptr, *panels_beta = nullptr;
+    int nitems = 0;
+    Bump* bump = nullptr;
+};
+
+static int ncols_for(int flags, int P) {
+    if (flags & WANT_D2MU) return 1 + P + P * (P + 1) / 2;
+    if (flags & WANT_DMU) return 1 + P;
+    return 1;
+}
+
+static int plan_build(gpd_ctx* c, gpd_model* const* models, int M, int flags, long long N, size_t extra_per_cand,
+                      size_t extra_fixed, Plan& pl) {
+    pl.models.assign(models, models + M);
+    pl.flags = flags;
+    pl.need_W = (flags & (WANT_DS2 | WANT_D2S2)) != 0;
+    pl.entries.clear();
+    pl.groups.clear();
+    pl.panel_unit = 0;
+    pl.max_nrhs = 1;
+    size_t per_cand = extra_per_cand;
+    std::map<std::tuple<int, int, int>, int> gidx;
+    for (int m = 0; m < M; ++m) {
+        gpd_model* mo = models[m];
+        GPD_CHECK(mo && mo->ctx == c, "model does not belong to this context");
+        GPD_CHECK(mo->has_pmean, "pmean is not set (surrogate_model.py:171)");
+        const int P = mo->P, E = mo->E, npair = P * (P + 1) / 2;
+        const int nrhs = pl.need_W ? 1 + P : 1;
+        pl.max_nrhs = std::max(pl.max_nrhs, nrhs);
+        for (int e = 0; e < E; ++e)
+            for (int r = 0; r < mo->R; ++r) {
+                gpd_gp* g = mo->gps[(size_t)e * mo->R + r];
+                if (!g) continue;
+                auto key = std::make_tuple(g->kernel, g->nx, P);
+                auto it = gidx.find(key);
+                int gi;
+                if (it == gidx.end()) {
+                    gi = (int)pl.groups.size();
+                    gidx[key] = gi;
+                    pl.groups.push_back(Group{g->kernel, g->nx, P, {}, 0, 0});
+                } else {
+                    gi = it->second;
+                }
+                pl.groups[gi].entries.push_back((int)pl.entries.size());
+                pl.entries.push_back(GpEntry{g, m, e, r, 0});
+                pl.panel_unit += g->n_pad;
+            }
+        // raws + hook outputs, bytes per candidate
+        const int ncols = ncols_for(flags, P);
+        const int ng = nrhs * (nrhs + 1) / 2;
+        size_t d = (size_t)E * (ncols + 1 + ng + ((flags & WANT_D2S2) ? npair : 0));
+        d += (size_t)E * 2;
+        if (flags & WANT_DMU) d += (size_t)E * P;
+        if (flags & WANT_D2MU) d += (size_t)E * P * P;
+        if (flags & WANT_DS2) d += (size_t)E * P;
+        if (flags & WANT_D2S2) d += (size_t)E * P * P;
+        per_cand += d * sizeof(double);
+        if (mo->nb) per_cand += sizeof(int) * mo->R;
+    }
+    GPD_CHECK(!pl.entries.empty(), "no GP surrogates in the models");
+    // panels: in (max_nrhs kinds), out (only when W is needed), beta (only for d2s2)
+    int kinds = pl.max_nrhs + (pl.need_W ? pl.max_nrhs : 0) + ((flags & WANT_D2S2) ? 1 : 0);
+    per_cand += (size_t)pl.panel_unit * kinds * sizeof(double);
+    pl.per_cand_bytes = per_cand;
+    const size_t fixed = extra_fixed + (size_t)(1 << 20) +
+                         pl.entries.size() * (sizeof(GpView) + 64) +
+                         (size_t)kBlk * per_cand;   // tile rounding slack
+    GPD_CHECK(c->scratch_limit > fixed + (size_t)kBlk * per_cand,
+              "scratch limit too small for one 128-candidate tile of these models; raise gpd_set_scratch_bytes");
+    long long chunk = (long long)((c->scratch_limit - fixed) / per_cand);
+    chunk = chunk / kBlk * kBlk;
+    const long long want = (N + kBlk - 1) / kBlk * kBlk;
+    chunk = std::min(chunk, want);
+    chunk = std::min<long long>(chunk, 1 << 22);
+    GPD_CHECK(chunk >= kBlk, "scratch limit too small");
+    pl.chunk = (int)chunk;
+    pl.tiles = pl.chunk / kBlk;
+    return 0;
+}
+
+// carve the scratch region and upload the static descriptor tables for this plan
+static int plan_materialize(gpd_ctx* c, Plan& pl, Bump& bump) {
+    const int M = (int)pl.models.size();
+    const int Nc = pl.chunk;
+    pl.mb.assign(M, ModelBufs());
+    std::vector<RawOut> raws(M);
+    for (int m = 0; m < M; ++m) {
+        gpd_model* mo = pl.models[m];
+        const int P = mo->P, E = mo->E, npair = P * (P + 1) / 2;
+        const int nrhs = pl.need_W ? 1 + P : 1;
+        ModelBufs& b = pl.mb[m];
+        b.ldraw = ncols_for(pl.flags, P);
+        b.ng = nrhs * (nrhs + 1) / 2;
+        b.raw.cmu = bump.take<double>((size_t)E * Nc * b.ldraw);
+        b.raw.kss = bump.take<double>((size_t)E * Nc);
+        b.raw.gram = bump.take<double>((size_t)E * Nc * b.ng);
+        b.raw.bh = (pl.flags & WANT_D2S2) ? bump.take<double>((size_t)E * Nc * npair) : nullptr;
+        b.mu = bump.take<double>((size_t)Nc * E);
+        b.ldmu = E;
+        b.s2 = bump.take<double>((size_t)Nc * E);
+        if (pl.flags & WANT_DMU) b.dmu = bump.take<double>((size_t)Nc * E * P);
+        if (pl.flags & WANT_D2MU) b.d2mu = bump.take<double>((size_t)Nc * E * P * P);
+        if (pl.flags & WANT_DS2) b.ds2 = bump.take<double>((size_t)Nc * E * P);
+        if (pl.flags & WANT_D2S2) b.d2s2 = bump.take<double>((size_t)Nc * E * P * P);
+        if (mo->nb) {
+            b.idx = bump.take<int>((size_t)mo->R * Nc);
+            b.counts = bump.take<int>(mo->R);
+        }
+        raws[m] = b.raw;
+    }
+    const size_t panel_doubles = (size_t)pl.panel_unit * Nc;
+    pl.panels_in = bump.take<double>(panel_doubles * pl.max_nrhs);
+    pl.panels_out = pl.need_W ? bump.take<double>(panel_doubles * pl.max_nrhs) : nullptr;
+    pl.panels_beta = (pl.flags & WANT_D2S2) ? bump.take<double>(panel_doubles) : nullptr;
+
+    // views, grouped so that each eval launch sees a contiguous item range
+    std::vector<GpView> views(pl.entries.size());
+    std::vector<Item> items;
+    long long off = 0;
+    for (auto& grp : pl.groups) {
+        grp.item_begin = (int)items.size();
+        for (int ei : grp.entries) {
+            GpEntry& en = pl.entries[ei];
+            gpd_gp* g = en.gp;
+            gpd_model* mo = pl.models[en.model];
+            en.panel_off = off;
+            off += (long long)pl.tiles * g->n_pad * kBlk;
+            GpView& v = views[ei];
+            memset(&v, 0, sizeof(v));
+            v.kernel = g->kernel;
+            v.n = g->n;
+            v.n_pad = g->n_pad;
+            v.nblk = g->nblk;
+            v.nx = g->nx;
+            v.P = g->P;
+            v.kss = g->var_x * g->var_p;
+            v.power_x = g->power_x;
+            v.Xs = g->Xs;
+            v.C = g->C;
+            v.G = g->G;
+            v.H = g->H;
+            v.LinvF = g->LinvF;
+            v.LinvB = g->LinvB;
+            for (int d = 0; d < g->nx; ++d) {
+                v.ls[d] = g->ls_x[d];
+                v.x_active[d] = g->x_active[d];
+                v.xmin[d] = pl.transformed ? 0.0 : mo->xmin[g->x_active[d]];
+                v.xdiff[d] = pl.transformed ? 1.0 : mo->xmax[g->x_active[d]] - mo->xmin[g->x_active[d]];
+            }
+            const ModelBufs& b = pl.mb[en.model];
+            v.idx = mo->nb ? b.idx + (size_t)en.r * Nc : nullptr;
+            v.count = mo->nb ? b.counts + en.r : nullptr;
+            v.out_e = en.e;
+            v.model = en.model;
+            v.panel_off = en.panel_off;
+            for (int t = 0; t < pl.tiles; ++t) items.push_back(Item{ei, t});
+        }
+        grp.item_count = (int)items.size() - grp.item_begin;
+    }
+    pl.nitems = (int)items.size();
+    pl.views_dev = bump.take<GpView>(views.size());
+    pl.items_dev = bump.take<Item>(items.size());
+    pl.raws_dev = bump.take<RawOut>(M);
+    GPD_CHECK(bump.off <= bump.cap, "internal: scratch plan overflow");
+    GPD_CUDA(cudaMemcpyAsync(pl.views_dev, views.data(), sizeof(GpView) * views.size(), cudaMemcpyHostToDevice, c->stream));
+    GPD_CUDA(cudaMemcpyAsync(pl.items_dev, items.data(), sizeof(Item) * items.size(), cudaMemcpyHostToDevice, c->stream));
+    GPD_CUDA(cudaMemcpyAsync(pl.raws_dev, raws.data(), sizeof(RawOut) * M, cudaMemcpyHostToDevice, c->stream));
+    GPD_CUDA(cudaStreamSynchronize(c->stream));   // the host vectors go out of scope
+    return 0;
+}
+
+// run the GP part for one chunk of nc candidates (device X, row stride ldx); results in pl.mb[m]
+static int run_chunk(gpd_ctx* c, Plan& pl, const double* X_dev, int ldx, int nc) {
+    cudaStream_t s = c->stream;
+    const int M = (int)pl.models.size();
+    const int Nc = pl.chunk;
+    const int tiles_used = (nc + kBlk - 1) / kBlk;
+    // routing + zero fill for models with binary variables (rows without a GP keep 0: gp_model.py:190-196)
+    for (int m = 0; m < M; ++m) {
+        gpd_model* mo = pl.models[m];
+        if (!mo->nb) continue;
+        ModelBufs& b = pl.mb[m];
+        Span sp(c, F_SETUP, 1, 0);
+        GPD_TRY(launch_route(s, X_dev, ldx, nc, mo->nb, mo->bcols_dev, mo->weights_dev, mo->R, b.idx, b.counts, Nc));
+        GPD_CUDA(cudaMemsetAsync(b.raw.cmu, 0, sizeof(double) * (size_t)mo->E * Nc * b.ldraw, s));
+        GPD_CUDA(cudaMemsetAsync(b.raw.kss, 0, sizeof(double) * (size_t)mo->E * Nc, s));
+        GPD_CUDA(cudaMemsetAsync(b.raw.gram, 0, sizeof(double) * (size_t)mo->E * Nc * b.ng, s));
+        if (b.raw.bh)
+            GPD_CUDA(cudaMemsetAsync(b.raw.bh, 0, sizeof(double) * (size_t)mo->E * Nc * (mo->P * (mo->P + 1) / 2), s));
+    }
+    // The item list holds pl.tiles tiles per GP; tiles beyond the chunk's candidates exit on the device
+    // count check (identity routing uses chunk_n = nc).
+    (void)tiles_used;
+    double n2sum = 0;   // algorithmic flops: n^2 per candidate per right-hand side
+    for (auto& grp : pl.groups) {
+        const int nrhs = pl.need_W ? 1 + grp.P : 1;
+        const int ncols = ncols_for(pl.flags, grp.P);
+        double evflops = 0;
+        for (int ei : grp.entries) {
+            const gpd_gp* g = pl.entries[ei].gp;
+            const double share = 1.0 / pl.models[pl.entries[ei].model]->R;
+            evflops += share * (double)nc * g->n * (3.0 * g->nx + 45.0 + 2.0 * ncols + nrhs);
+            n2sum += share * (double)nc * (double)g->n * g->n * nrhs;
+        }
+        Span sp(c, F_EVAL, 1, evflops);
+        GPD_TRY(launch_eval(s, pl.views_dev, pl.items_dev + grp.item_begin, grp.item_count, X_dev, ldx, nc, nrhs, ncols,
+                            grp.kernel, grp.nx, pl.panels_in, pl.raws_dev, pl.mb[pl.entries[grp.entries[0]].model].ldraw));
+    }
+    if (!pl.need_W) {
+        Span sp(c, F_TRI, 1, n2sum);
+        GPD_TRY(launch_tri(s, pl.views_dev, pl.items_dev, pl.nitems, 1, 1, 1, 0, pl.panels_in, nullptr, pl.raws_dev, 1, nc,
+                           c->num_sms, c->tri_variant));
+    } else {
+        for (auto& grp : pl.groups) {
+            const int nrhs = 1 + grp.P;
+            double fl = 0, flb = 0;
+            for (int ei : grp.entries) {
+                const gpd_gp* g = pl.entries[ei].gp;
+                const double share = 1.0 / pl.models[pl.entries[ei].model]->R;
+                fl += share * (double)nc * (double)g->n * g->n * nrhs;
+                flb += share * (double)nc * (double)g->n * g->n;
+            }
+            {
+                Span sp(c, F_TRI, 1, fl);
+                GPD_TRY(launch_tri(s, pl.views_dev, pl.items_dev + grp.item_begin, grp.item_count, nrhs, nrhs, nrhs, 0,
+                                   pl.panels_in, pl.panels_out, nullptr, 0, nc, c->num_sms, c->tri_variant));
+            }
+            {
+                Span sp(c, F_GRAM, 1, fl / (double)std::max(1, pl.entries[grp.entries[0]].gp->n) * (nrhs + 1));
+                GPD_TRY(launch_gram(s, pl.views_dev, pl.items_dev + grp.item_begin, grp.item_count, nrhs, pl.panels_out,
+                                    pl.raws_dev, nc));
+            }
+            if (pl.flags & WANT_D2S2) {
+                {
+                    Span sp(c, F_TRI, 1, flb);
+                    GPD_TRY(launch_tri(s, pl.views_dev, pl.items_dev + grp.item_begin, grp.item_count, 1, nrhs, 1, 1,
+                                       pl.panels_out, pl.panels_beta, nullptr, 0, nc, c->num_sms, c->tri_variant));
+                }
+                Span sp(c, F_EVAL, 1, 0);
+                GPD_TRY(launch_beta_contract(s, pl.views_dev, pl.items_dev + grp.item_begin, grp.item_count, X_dev, ldx, nc,
+                                             grp.kernel, grp.nx, grp.P, pl.panels_beta, pl.raws_dev));
+            }
+        }
+    }
+    for (int m = 0; m < M; ++m) {
+        gpd_model* mo = pl.models[m];
+        ModelBufs& b = pl.mb[m];
+        Span sp(c, F_MARG, 1, 0);
+        GPD_TRY(launch_finalize(s, mo->xf_dev + (pl.transformed ? 1 : 0), pl.raws_dev, m, mo->E, mo->P, nc, b.ldraw, pl.flags,
+                                pl.need_W ? 1 + mo->P : 1, b.mu, b.ldmu, b.s2, b.dmu, b.d2mu, b.ds2, b.d2s2));
+    }
+    return 0;
+}
+
+static int ensure_scratch(gpd_ctx* c, size_t bytes) {
+    GPD_CHECK(bytes <= c->scratch_limit + (64u << 20), "internal: plan exceeds the scratch limit");
+    return c->scratch.ensure(bytes);
+}
+
+static int upload_model_state(gpd_model* mo);
+
+}  // namespace gpd
+
+// =================================================================================================
+// context
+// =================================================================================================
+extern "C" {
+
+const char* gpd_last_error(void) { return g_error.c_str(); }
+
+int gpd_create(int device, gpd_ctx** out) {
+    GPD_CHECK(out, "null out pointer");
+    *out = nullptr;
+    int count = 0;
+    GPD_CUDA(cudaGetDeviceCount(&count));
+    GPD_CHECK(count > 0 && device >= 0 && device < count, "no such CUDA device (this library has no CPU fallback)");
+    GPD_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GPD_CUDA(cudaGetDeviceProperties(&prop, device));
+    GPD_CHECK(prop.major == 10, "libgpdoemd_b200 is built for sm_100a (Blackwell B200) only");
+    gpd_ctx* c = new gpd_ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    GPD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    GPD_CUDA(cudaEventCreate(&c->t0));
+    GPD_CUDA(cudaEventCreate(&c->t1));
+    GPD_CUDA(cudaMalloc(&c->best_val_dev, sizeof(double)));
+    GPD_CUDA(cudaMalloc(&c->best_idx_dev, sizeof(long long)));
+    GPD_CUDA(cudaMalloc(&c->argmax_partial, argmax_partial_bytes()));
+    *out = c;
+    return 0;
+}
+
+void gpd_destroy(gpd_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->scratch.release();
+    c->tables.release();
+    c->flush.release();
+    for (auto& s : c->spans) {
+        cudaEventDestroy(s.a);
+        cudaEventDestroy(s.b);
+    }
+    for (auto e : c->pool) cudaEventDestroy(e);
+    cudaEventDestroy(c->t0);
+    cudaEventDestroy(c->t1);
+    cudaFree(c->best_val_dev);
+    cudaFree(c->best_idx_dev);
+    cudaFree(c->argmax_partial);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int gpd_set_scratch_bytes(gpd_ctx* c, uint64_t bytes) {
+    GPD_CHECK(c, "null context");
+    GPD_CHECK(bytes >= (64ull << 20), "scratch must be at least 64 MiB");
+    GPD_CUDA(cudaSetDevice(c->device));
+    c->scratch_limit = bytes;
+    if (c->scratch.cap > bytes) {
+        GPD_CUDA(cudaStreamSynchronize(c->stream));
+        c->scratch.release();
+    }
+    return 0;
+}
+
+int gpd_set_option(gpd_ctx* c, const char* name, int64_t value) {
+    GPD_CHECK(c && name, "null argument");
+    if (!strcmp(name, "tri_variant")) {
+        GPD_CHECK(value == 0 || value == 1, "tri_variant is 0 (16 consumer warps) or 1 (8 consumer warps)");
+        c->tri_variant = (int)value;
+        return 0;
+    }
+    set_error(std::string("unknown option ") + name);
+    return 2;
+}
+
+uint64_t gpd_launch_count(gpd_ctx* c) { return c ? c->launches : 0; }
+
+int gpd_profile_enable(gpd_ctx* c, int on) {
+    GPD_CHECK(c, "null context");
+    GPD_CUDA(cudaSetDevice(c->device));
+    GPD_TRY(resolve_spans(c));
+    c->profile = on;
+    for (int i = 0; i < GPD_NFAMILIES; ++i) {
+        c->fam_ms[i] = 0;
+        c->fam_flops[i] = 0;
+        c->fam_launches[i] = 0;
+    }
+    return 0;
+}
+
+int gpd_profile_read(gpd_ctx* c, double ms_out[GPD_NFAMILIES], uint64_t launches_out[GPD_NFAMILIES],
+                     double flops_out[GPD_NFAMILIES]) {
+    GPD_CHECK(c, "null context");
+    GPD_CUDA(cudaSetDevice(c->device));
+    GPD_TRY(resolve_spans(c));
+    for (int i = 0; i < GPD_NFAMILIES; ++i) {
+        if (ms_out) ms_out[i] = c->fam_ms[i];
+        if (launches_out) launches_out[i] = c->fam_launches[i];
+        if (flops_out) flops_out[i] = c->fam_flops[i];
+    }
+    return 0;
+}
+
+int gpd_timer_start(gpd_ctx* c) {
+    GPD_CHECK(c, "null context");
+    GPD_CUDA(cudaSetDevice(c->device));
+    GPD_CUDA(cudaEventRecord(c->t0, c->stream));
+    return 0;
+}
+int gpd_timer_stop(gpd_ctx* c, double* ms_out) {
+    GPD_CHECK(c && ms_out, "null argument");
+    GPD_CUDA(cudaSetDevice(c->device));
+    GPD_CUDA(cudaEventRecord(c->t1, c->stream));
+    GPD_CUDA(cudaEventSynchronize(c->t1));
+    float ms = 0.f;
+    GPD_CUDA(cudaEventElapsedTime(&ms, c->t0, c->t1));
+    *ms_out = ms;
+    return 0;
+}
+int gpd_sync(gpd_ctx* c) {
+    GPD_CHECK(c, "null context");
+    GPD_CUDA(cudaSetDevice(c->device));
+    GPD_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int gpd_probe_fp64_peak(gpd_ctx* c, double* tflops_out) {
+    GPD_CHECK(c && tflops_out, "null argument");
+    GPD_CUDA(cudaSetDevice(c->device));
+    const int iters = 4096;
+    double* sink = nullptr;
+    GPD_CUDA(cudaMalloc(&sink, sizeof(double) * c->num_sms * 2 * 256));
+    cudaEvent_t a, b;
+    GPD_CUDA(cudaEventCreate(&a));
+    GPD_CUDA(cudaEventCreate(&b));
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        GPD_CUDA(cudaEventRecord(a, c->stream));
+        GPD_TRY(launch_dmma_probe(c->stream, c->num_sms, iters, sink));
+        c->launches += 1;
+        GPD_CUDA(cudaEventRecord(b, c->stream));
+        GPD_CUDA(cudaEventSynchronize(b));
+        float ms = 0.f;
+        GPD_CUDA(cudaEventElapsedTime(&ms, a, b));
+        // per warp and iteration: 8 independent m8n8k4 DMMA = 8 * 512 flops
+        const double flops = (double)c->num_sms * 2 * 8 /*warps*/ * (double)iters * 8 * 512;
+        if (rep) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(sink);
+    *tflops_out = best;
+    return 0;
+}
+
+int gpd_flush_l2(gpd_ctx* c) {
+    GPD_CHECK(c, "null context");
+    GPD_CUDA(cudaSetDevice(c->device));
+    const size_t n = (256ull << 20) / sizeof(double);   // 256 MiB > 126 MB L2
+    if (!c->flush.p) {
+        GPD_TRY(c->flush.ensure(n * sizeof(double)));
+        GPD_CUDA(cudaMemsetAsync(c->flush.p, 0, n * sizeof(double), c->stream));
+    }
+    GPD_TRY(launch_flush(c->stream, (double*)c->flush.p, n));
+    return 0;
+}
+
+// ---- device buffer helpers ----------------------------------------------------------------------
+int gpd_dev_alloc(gpd_ctx* c, uint64_t bytes, void** out_dev) {
+    GPD_CHECK(c && out_dev, "null argument");
+    GPD_CUDA(cudaSetDevice(c->device));
+    GPD_CUDA(cudaMalloc(out_dev, bytes ? bytes : 8));
+    return 0;
+}
+int gpd_dev_free(gpd_ctx* c, void* dev) {
+    GPD_CHECK(c, "null context");
+    GPD_CUDA(cudaSetDevice(c->device));
+    GPD_CUDA(cudaStreamSynchronize(c->stream));
+    GPD_CUDA(cudaFree(dev));
+    return 0;
+}
+int gpd_dev_upload(gpd_ctx* c, void* dst_dev, const void* src_host, uint64_t bytes) {
+    GPD_CHECK(c, "null context");
+    GPD_CUDA(cudaSetDevice(c->device));
+    GPD_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, c->stream));
+    GPD_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int gpd_dev_download(gpd_ctx* c, void* dst_host, const void* src_dev, uint64_t bytes) {
+    GPD_CHECK(c, "null context");
+    GPD_CUDA(cudaSetDevice(c->device));
+    GPD_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+    GPD_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int gpd_host_alloc_pinned(gpd_ctx* c, uint64_t bytes, void** out_host) {
+    GPD_CHECK(c && out_host, "null argument");
+    GPD_CUDA(cudaSetDevice(c->device));
+    GPD_CUDA(cudaHostAlloc(out_host, bytes ? bytes : 8, cudaHostAllocDefault));
+    return 0;
+}
+int gpd_host_free_pinned(gpd_ctx* c, void* host) {
+    GPD_CHECK(c, "null context");
+    GPD_CUDA(cudaFreeHost(host));
+    return 0;
+}
+int gpd_dev_fill_uniform(gpd_ctx* c, double* X_dev, int64_t N, int32_t D, uint64_t seed, int64_t first_row,
+                         const double* lo, const double* hi) {
+    GPD_CHECK(c && X_dev && lo && hi, "null argument");
+    GPD_CHECK(D >= 1 && D <= 64 && N >= 0, "bad shape");
+    GPD_CUDA(cudaSetDevice(c->device));
+    if (N == 0) return 0;
+    GPD_TRY(c->tables.ensure(sizeof(double) * 128));
+    double* lo_dev = (double*)c->tables.p;
+    double* hi_dev = lo_dev + 64;
+    GPD_CUDA(cudaMemcpyAsync(lo_dev, lo, sizeof(double) * D, cudaMemcpyHostToDevice, c->stream));
+    GPD_CUDA(cudaMemcpyAsync(hi_dev, hi, sizeof(double) * D, cudaMemcpyHostToDevice, c->stream));
+    Span sp(c, F_SETUP, 1, 0);
+    GPD_TRY(launch_fill_uniform(c->stream, X_dev, N, D, seed, first_row, lo_dev, hi_dev));
+    return 0;
+}
+
+// =================================================================================================
+// GP state
+// =================================================================================================
+void gpd_gp_free(gpd_gp* g) {
+    if (!g) return;
+    cudaSetDevice(g->ctx->device);
+    cudaStreamSynchronize(g->ctx->stream);
+    cudaFree(g->Xs);
+    cudaFree(g->Zp);
+    cudaFree(g->alpha);
+    cudaFree(g->ls_p);
+    cudaFree(g->C);
+    cudaFree(g->G);
+    cudaFree(g->H);
+    cudaFree(g->LinvF);
+    cudaFree(g->LinvB);
+    delete g;
+}
+
+int gpd_gp_upload(gpd_ctx* c, const gpd_gp_desc* d, gpd_gp** out) {
+    GPD_CHECK(c && d && out, "null argument");
+    *out = nullptr;
+    GPD_CHECK(d->kernel >= 0 && d->kernel <= 5, "unknown kernel id");
+    GPD_CHECK(d->n >= 1, "empty training set");
+    GPD_CHECK(d->dim_p >= 1 && d->dim_p <= kMaxP, "dim_p out of range (1..16)");
+    GPD_CHECK(d->n_x_active >= 1 && d->n_x_active <= kMaxXDims, "x-kernel acts on 1..8 non-binary design dimensions");
+    GPD_CHECK(d->dim_x >= d->n_x_active, "dim_x smaller than the number of active dimensions");
+    GPD_CHECK(d->x_active && d->ls_x && d->ls_p && d->Z && d->alpha && d->L, "null array in descriptor");
+    GPD_CUDA(cudaSetDevice(c->device));
+    gpd_gp* g = new gpd_gp();
+    g->ctx = c;
+    g->kernel = d->kernel;
+    g->n = d->n;
+    g->n_pad = (d->n + kBlk - 1) / kBlk * kBlk;
+    g->nblk = g->n_pad / kBlk;
+    g->D = d->dim_x;
+    g->P = d->dim_p;
+    g->nx = d->n_x_active;
+    g->var_x = d->var_x;
+    g->var_p = d->var_p;
+    g->power_x = d->power_x;
+    g->power_p = d->power_p;
+    const int n = g->n, n_pad = g->n_pad, P = g->P, nx = g->nx, dz = g->D + g->P;
+    for (int k = 0; k < nx; ++k) {
+        g->x_active[k] = d->x_active[k];
+        g->ls_x[k] = d->ls_x[k];
+        if (!(d->x_active[k] >= 0 && d->x_active[k] < g->D) || !(d->ls_x[k] > 0)) {
+            delete g;
+            set_error("bad active dimension or non-positive lengthscale");
+            return 2;
+        }
+    }
+    const int npair = P * (P + 1) / 2;
+    std::vector<double> Xs((size_t)n_pad * nx, 0.0), Zp((size_t)n * P);
+    for (int i = 0; i < n; ++i) {
+        for (int k = 0; k < nx; ++k) Xs[(size_t)i * nx + k] = d->Z[(size_t)i * dz + d->x_active[k]] / d->ls_x[k];
+        for (int a = 0; a < P; ++a) Zp[(size_t)i * P + a] = d->Z[(size_t)i * dz + g->D + a];
+    }
+    cudaStream_t s = c->stream;
+    int rc = 0;
+    auto fail = [&](int code) {
+        gpd_gp_free(g);
+        return code;
+    };
+#define GP_CUDA(call)                                                                       \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e__));                 \
+            return fail(1);                                                                 \
+        }                                                                                   \
+    } while (0)
+    GP_CUDA(cudaMalloc(&g->Xs, sizeof(double) * Xs.size()));
+    GP_CUDA(cudaMalloc(&g->Zp, sizeof(double) * Zp.size()));
+    GP_CUDA(cudaMalloc(&g->alpha, sizeof(double) * n));
+    GP_CUDA(cudaMalloc(&g->ls_p, sizeof(double) * P));
+    GP_CUDA(cudaMalloc(&g->C, sizeof(double) * (size_t)(1 + P + npair) * n_pad));
+    GP_CUDA(cudaMalloc(&g->G, sizeof(double) * (size_t)(1 + P) * n_pad));
+    GP_CUDA(cudaMalloc(&g->H, sizeof(double) * (size_t)std::max(1, npair) * n_pad));
+    const size_t pack_bytes = sizeof(double) * (size_t)packed_tiles(g->nblk) * kTileElems;
+    GP_CUDA(cudaMalloc(&g->LinvF, pack_bytes));
+    GP_CUDA(cudaMalloc(&g->LinvB, pack_bytes));
+    GP_CUDA(cudaMemcpyAsync(g->Xs, Xs.data(), sizeof(double) * Xs.size(), cudaMemcpyHostToDevice, s));
+    GP_CUDA(cudaMemcpyAsync(g->Zp, Zp.data(), sizeof(double) * Zp.size(), cudaMemcpyHostToDevice, s));
+    GP_CUDA(cudaMemcpyAsync(g->alpha, d->alpha, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    GP_CUDA(cudaMemcpyAsync(g->ls_p, d->ls_p, sizeof(double) * P, cudaMemcpyHostToDevice, s));
+    // factor: upload L, invert on the device, pack forward and backward operands
+    double *L_dev = nullptr, *dense = nullptr;
+    GP_CUDA(cudaMalloc(&L_dev, sizeof(double) * (size_t)n * n));
+    if (cudaMalloc(&dense, sizeof(double) * (size_t)n_pad * n_pad) != cudaSuccess) {
+        cudaFree(L_dev);
+        set_error("out of device memory for the factor inversion workspace");
+        return fail(1);
+    }
+    cudaError_t e1 = cudaMemcpyAsync(L_dev, d->L, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, s);
+    if (e1 == cudaSuccess) {
+        uint64_t nl = 0;
+        rc = launch_invert_and_pack(s, L_dev, n, n_pad, dense, g->LinvF, g->LinvB, &nl);
+        c->launches += nl;
+        if (c->profile) c->fam_launches[F_SETUP] += nl;
+    }
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    cudaFree(L_dev);
+    cudaFree(dense);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || rc) {
+        if (!rc) set_error(std::string("factor upload/inversion failed: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        return fail(1);
+    }
+#undef GP_CUDA
+    *out = g;
+    return 0;
+}
+
+// =================================================================================================
+// model
+// =================================================================================================
+void gpd_model_free(gpd_model* mo) {
+    if (!mo) return;
+    cudaSetDevice(mo->ctx->device);
+    cudaStreamSynchronize(mo->ctx->stream);
+    cudaFree(mo->xf_dev);
+    cudaFree(mo->pstar_dev);
+    cudaFree(mo->bcols_dev);
+    cudaFree(mo->weights_dev);
+    delete mo;
+}
+
+int gpd_model_create(gpd_ctx* c, int32_t E, int32_t dim_x, int32_t dim_p, int32_t n_binary, const int32_t* binary,
+                     gpd_gp* const* gps, const double* xmin, const double* xmax, const double* pmin,
+                     const double* pmax, const double* ymean, const double* ystd, gpd_model** out) {
+    GPD_CHECK(c && out && gps && xmin && xmax && pmin && pmax && ymean && ystd, "null argument");
+    *out = nullptr;
+    GPD_CHECK(E >= 1 && E <= kMaxE, "num_outputs out of range (1..8)");
+    GPD_CHECK(dim_p >= 1 && dim_p <= kMaxP, "dim_p out of range (1..16)");
+    GPD_CHECK(dim_x >= 1 && dim_x <= 64, "dim_x out of range");
+    GPD_CHECK(n_binary >= 0 && n_binary <= kMaxBinary && (n_binary == 0 || binary), "bad binary variable list");
+    GPD_CUDA(cudaSetDevice(c->device));
+    gpd_model* mo = new gpd_model();
+    mo->ctx = c;
+    mo->E = E;
+    mo->D = dim_x;
+    mo->P = dim_p;
+    mo->nb = n_binary;
+    mo->R = 1 << n_binary;
+    for (int v = 0; v < n_binary; ++v) mo->binary[v] = binary[v];
+    mo->gps.assign(gps, gps + (size_t)E * mo->R);
+    int live = 0;
+    for (gpd_gp* g : mo->gps) {
+        if (!g) continue;
+        ++live;
+        if (g->ctx != c || g->D != dim_x || g->P != dim_p) {
+            delete mo;
+            set_error("GP handle does not match the model (context, dim_x or dim_p)");
+            return 2;
+        }
+    }
+    if (!live) {
+        delete mo;
+        set_error("model without any GP");
+        return 2;
+    }
+    mo->xmin.assign(xmin, xmin + dim_x);
+    mo->xmax.assign(xmax, xmax + dim_x);
+    mo->pmin.assign(pmin, pmin + dim_p);
+    mo->pmax.assign(pmax, pmax + dim_p);
+    mo->ymean.assign(ymean, ymean + E);
+    mo->ystd.assign(ystd, ystd + E);
+    mo->pmean.assign(dim_p, 0.0);
+    mo->Sigma.assign((size_t)dim_p * dim_p, 0.0);
+    cudaError_t err = cudaMalloc(&mo->xf_dev, 2 * sizeof(ModelXform));
+    if (err == cudaSuccess) err = cudaMalloc(&mo->pstar_dev, sizeof(double) * dim_p);
+    if (err == cudaSuccess && n_binary) {
+        err = cudaMalloc(&mo->bcols_dev, sizeof(int) * n_binary);
+        if (err == cudaSuccess) err = cudaMalloc(&mo->weights_dev, sizeof(int) * n_binary);
+        if (err == cudaSuccess) {
+            int w[kMaxBinary];
+            for (int v = 0; v < n_binary; ++v) w[v] = binary_combo_weight(n_binary, v);
+            err = cudaMemcpy(mo->bcols_dev, mo->binary, sizeof(int) * n_binary, cudaMemcpyHostToDevice);
+            if (err == cudaSuccess) err = cudaMemcpy(mo->weights_dev, w, sizeof(int) * n_binary, cudaMemcpyHostToDevice);
+        }
+    }
+    if (err != cudaSuccess) {
+        set_error(std::string("model allocation failed: ") + cudaGetErrorString(err));
+        gpd_model_free(mo);
+        return 1;
+    }
+    *out = mo;
+    return 0;
+}
+
+int gpd_model_set_pmean_sigma(gpd_model* mo, const double* pmean, const double* Sigma) {
+    GPD_CHECK(mo && pmean, "null argument");
+    gpd_ctx* c = mo->ctx;
+    GPD_CUDA(cudaSetDevice(c->device));
+    const int P = mo->P;
+    mo->pmean.assign(pmean, pmean + P);
+    mo->has_pmean = true;
+    if (Sigma) {
+        mo->Sigma.assign(Sigma, Sigma + (size_t)P * P);
+        mo->has_sigma = true;
+    }
+    mo->pstar.resize(P);
+    for (int a = 0; a < P; ++a)   // trans_p(pmean), surrogate_model.py:175
+        mo->pstar[a] = (mo->pmean[a] - mo->pmin[a]) / (mo->pmax[a] - mo->pmin[a]);
+    return upload_model_state(mo);
+}
+
+int gpd_model_set_pstar(gpd_model* mo, const double* pstar) {
+    GPD_CHECK(mo && pstar, "null argument");
+    GPD_CUDA(cudaSetDevice(mo->ctx->device));
+    const int P = mo->P;
+    mo->pstar.assign(pstar, pstar + P);
+    for (int a = 0; a < P; ++a) mo->pmean[a] = mo->pmin[a] + pstar[a] * (mo->pmax[a] - mo->pmin[a]);
+    mo->has_pmean = true;
+    return upload_model_state(mo);
+}
+
+}  // extern "C"
+
+namespace gpd {
+static int upload_model_state(gpd_model* mo) {
+    gpd_ctx* c = mo->ctx;
+    const int P = mo->P, E = mo->E;
+    ModelXform xf[2];
+    memset(xf, 0, sizeof(xf));
+    for (int k = 0; k < 2; ++k) {
+        xf[k].E = E;
+        xf[k].P = P;
+    }
+    for (int e = 0; e < E; ++e) {
+        xf[0].ymean[e] = mo->ymean[e];
+        xf[0].ystd[e] = mo->ystd[e];
+        xf[1].ymean[e] = 0.0;
+        xf[1].ystd[e] = 1.0;
+    }
+    for (int a = 0; a < P; ++a) {
+        xf[0].pdiff[a] = mo->pmax[a] - mo->pmin[a];
+        xf[1].pdiff[a] = 1.0;
+    }
+    for (int k = 0; k < P * P; ++k) xf[0].Sigma[k] = xf[1].Sigma[k] = mo->Sigma[k];
+    cudaStream_t s = c->stream;
+    GPD_CUDA(cudaMemcpyAsync(mo->xf_dev, xf, sizeof(xf), cudaMemcpyHostToDevice, s));
+    GPD_CUDA(cudaMemcpyAsync(mo->pstar_dev, mo->pstar.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
+    for (gpd_gp* g : mo->gps) {
+        if (!g) continue;
+        Span sp(c, F_SETUP, 1, 0);
+        GPD_TRY(launch_pstate(s, g->kernel, g->n, g->n_pad, P, P, g->Zp, g->alpha, mo->pstar_dev, g->ls_p, g->var_x,
+                              g->var_p, g->power_p, g->C, g->G, g->H));
+    }
+    GPD_CUDA(cudaStreamSynchronize(s));   // xf is a stack copy
+    return 0;
+}
+
+// ---- shared driver for the hook-style entry points: host X in, host arrays out ------------------
+struct HostOut {
+    double *mu = nullptr, *s2 = nullptr, *dmu = nullptr, *d2mu = nullptr, *ds2 = nullptr, *d2s2 = nullptr;
+};
+
+static int hooks_host(gpd_model* mo, const double* X, int64_t N, int flags, const HostOut& o, bool transformed = false) {
+    GPD_CHECK(mo && (X || N == 0), "null argument");
+    GPD_CHECK(N >= 0, "negative N");
+    gpd_ctx* c = mo->ctx;
+    GPD_CUDA(cudaSetDevice(c->device));
+    if (N == 0) return 0;
+    Plan pl;
+    pl.transformed = transformed;
+    const int D = mo->D, E = mo->E, P = mo->P;
+    GPD_TRY(plan_build(c, &mo, 1, flags, N, sizeof(double) * D, 0, pl));
+    const size_t total = pl.per_cand_bytes * ((size_t)pl.chunk + kBlk) + (8u << 20) + pl.entries.size() * sizeof(GpView) +
+                         (size_t)pl.entries.size() * pl.tiles * sizeof(Item);
+    GPD_TRY(ensure_scratch(c, total));
+    Bump bump(c->scratch.p, c->scratch.cap);
+    double* X_dev = bump.take<double>((size_t)pl.chunk * D);
+    GPD_TRY(plan_materialize(c, pl, bump));
+    cudaStream_t s = c->stream;
+    for (int64_t start = 0; start < N; start += pl.chunk) {
+        const int nc = (int)std::min<int64_t>(pl.chunk, N - start);
+        GPD_CUDA(cudaMemcpyAsync(X_dev, X + (size_t)start * D, sizeof(double) * (size_t)nc * D, cudaMemcpyHostToDevice, s));
+        GPD_TRY(run_chunk(c, pl, X_dev, D, nc));
+        const ModelBufs& b = pl.mb[0];
+        auto down = [&](double* host, const double* dev, size_t per) -> cudaError_t {
+            if (!host) return cudaSuccess;
+            return cudaMemcpyAsync(host + (size_t)start * per, dev, sizeof(double) * (size_t)nc * per, cudaMemcpyDeviceToHost, s);
+        };
+        GPD_CUDA(down(o.mu, b.mu, E));
+        GPD_CUDA(down(o.s2, b.s2, E));
+        GPD_CUDA(down(o.dmu, b.dmu, (size_t)E * P));
+        GPD_CUDA(down(o.d2mu, b.d2mu, (size_t)E * P * P));
+        GPD_CUDA(down(o.ds2, b.ds2, (size_t)E * P));
+        GPD_CUDA(down(o.d2s2, b.d2s2, (size_t)E * P * P));
+        GPD_CUDA(cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+}  // namespace gpd
+
+extern "C" {
+
+int gpd_predict(gpd_model* mo, const double* X, int64_t N, double* M_out, double* S_out) {
+    HostOut o;
+    o.mu = M_out;
+    o.s2 = S_out;
+    return hooks_host(mo, X, N, 0, o);
+}
+int gpd_dmu_dp(gpd_model* mo, const double* X, int64_t N, double* out) {
+    GPD_CHECK(out || N == 0, "null output");
+    HostOut o;
+    o.dmu = out;
+    return hooks_host(mo, X, N, WANT_DMU, o);
+}
+int gpd_d2mu_dp2(gpd_model* mo, const double* X, int64_t N, double* out) {
+    GPD_CHECK(out || N == 0, "null output");
+    HostOut o;
+    o.d2mu = out;
+    return hooks_host(mo, X, N, WANT_D2MU, o);
+}
+int gpd_ds2_dp(gpd_model* mo, const double* X, int64_t N, double* out) {
+    GPD_CHECK(out || N == 0, "null output");
+    HostOut o;
+    o.ds2 = out;
+    return hooks_host(mo, X, N, WANT_DS2, o);
+}
+int gpd_d2s2_dp2(gpd_model* mo, const double* X, int64_t N, double* out) {
+    GPD_CHECK(out || N == 0, "null output");
+    HostOut o;
+    o.d2s2 = out;
+    return hooks_host(mo, X, N, WANT_D2S2, o);
+}
+/* all hooks in one pass (any output may be NULL): what a caching host wrapper calls once per X */
+int gpd_hooks(gpd_model* mo, const double* X, int64_t N, int32_t transformed, double* mu, double* s2, double* dmu,
+              double* d2mu, double* ds2, double* d2s2) {
+    HostOut o;
+    o.mu = mu;
+    o.s2 = s2;
+    o.dmu = dmu;
+    o.d2mu = d2mu;
+    o.ds2 = ds2;
+    o.d2s2 = d2s2;
+    int flags = (dmu ? WANT_DMU : 0) | (d2mu ? WANT_D2MU : 0) | (ds2 ? WANT_DS2 : 0) | (d2s2 ? WANT_D2S2 : 0);
+    return hooks_host(mo, X, N, flags, o, transformed != 0);
+}
+
+// =================================================================================================
+// marginals, criteria, argmax
+// =================================================================================================
+static int order_flags(int order) { return order == 1 ? WANT_DMU : (WANT_DMU | WANT_D2MU | WANT_D2S2); }
+
+int gpd_marginal(gpd_model* mo, const double* X, int64_t N, int order, double* mu_out, double* S_out) {
+    GPD_CHECK(mo && (X || N == 0) && (N == 0 || (mu_out && S_out)), "null argument");
+    GPD_CHECK(order == 1 || order == 2, "order must be 1 or 2");
+    GPD_CHECK(mo->has_sigma, "Sigma is not set (taylor_first_order.py:38 reads model.Sigma)");
+    gpd_ctx* c = mo->ctx;
+    GPD_CUDA(cudaSetDevice(c->device));
+    if (N == 0) return 0;
+    const int D = mo->D, E = mo->E, P = mo->P;
+    Plan pl;
+    const size_t extra = sizeof(double) * ((size_t)D + (size_t)E * E + (order == 2 ? (size_t)E * P * P + E : 0));
+    GPD_TRY(plan_build(c, &mo, 1, order_flags(order), N, extra, 0, pl));
+    const size_t total = pl.per_cand_bytes * ((size_t)pl.chunk + kBlk) + (8u << 20) + pl.entries.size() * sizeof(GpView) +
+                         (size_t)pl.entries.size() * pl.tiles * sizeof(Item);
+    GPD_TRY(ensure_scratch(c, total));
+    Bump bump(c->scratch.p, c->scratch.cap);
+    double* X_dev = bump.take<double>((size_t)pl.chunk * D);
+    double* S_dev = bump.take<double>((size_t)pl.chunk * E * E);
+    double* tmpA = order == 2 ? bump.take<double>((size_t)pl.chunk * E * P * P) : nullptr;
+    double* tmp_s2 = order == 2 ? bump.take<double>((size_t)pl.chunk * E) : nullptr;
+    GPD_TRY(plan_materialize(c, pl, bump));
+    cudaStream_t s = c->stream;
+    const double* Sigma_dev = (const double*)((const char*)mo->xf_dev + offsetof(ModelXform, Sigma));
+    for (int64_t start = 0; start < N; start += pl.chunk) {
+        const int nc = (int)std::min<int64_t>(pl.chunk, N - start);
+        GPD_CUDA(cudaMemcpyAsync(X_dev, X + (size_t)start * D, sizeof(double) * (size_t)nc * D, cudaMemcpyHostToDevice, s));
+        GPD_TRY(run_chunk(c, pl, X_dev, D, nc));
+        const ModelBufs& b = pl.mb[0];
+        {
+            Span sp(c, F_MARG, order == 2 ? 2 : 1, 0);
+            GPD_TRY(launch_assemble(s, order, nc, E, P, b.mu, E, b.s2, b.dmu, b.d2mu, b.d2s2, Sigma_dev, S_dev, E * E, tmpA,
+                                    tmp_s2));
+        }
+        GPD_CUDA(cudaMemcpyAsync(mu_out + (size_t)start * E, b.mu, sizeof(double) * (size_t)nc * E, cudaMemcpyDeviceToHost, s));
+        GPD_CUDA(cudaMemcpyAsync(S_out + (size_t)start * E * E, S_dev, sizeof(double) * (size_t)nc * E * E,
+                                 cudaMemcpyDeviceToHost, s));
+        GPD_CUDA(cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
+int gpd_marginal_assemble(gpd_ctx* c, int order, int64_t N, int32_t E, int32_t P, double* mu_io, const double* s2,
+                          const double* dmu, const double* ddmu, const double* dds2, const double* Sigma,
+                          double* S_out) {
+    GPD_CHECK(c && (N == 0 || (mu_io && s2 && dmu && Sigma && S_out)), "null argument");
+    GPD_CHECK(order == 1 || order == 2, "order must be 1 or 2");
+    GPD_CHECK(order == 1 || N == 0 || (ddmu && dds2), "second order needs ddmu and dds2");
+    GPD_CHECK(E >= 1 && E <= 64 && P >= 1 && P <= 64, "bad shape");
+    GPD_CUDA(cudaSetDevice(c->device));
+    if (N == 0) return 0;
+    const size_t per = sizeof(double) * ((size_t)2 * E + (size_t)E * P + (size_t)E * E +
+                                         (order == 2 ? (size_t)3 * E * P * P + E : 0));
+    int64_t chunk = std::min<int64_t>(N, std::max<int64_t>(1, (int64_t)((c->scratch_limit - (1 << 20)) / per)));
+    chunk = std::min<int64_t>(chunk, 1 << 24);
+    GPD_TRY(ensure_scratch(c, per * (size_t)chunk + (1 << 20)));
+    Bump bump(c->scratch.p, c->scratch.cap);
+    double* d_mu = bump.take<double>((size_t)chunk * E);
+    double* d_s2 = bump.take<double>((size_t)chunk * E);
+    double* d_dmu = bump.take<double>((size_t)chunk * E * P);
+    double* d_S = bump.take<double>((size_t)chunk * E * E);
+    double *d_ddmu = nullptr, *d_dds2 = nullptr, *tmpA = nullptr, *tmp_s2 = nullptr;
+    if (order == 2) {
+        d_ddmu = bump.take<double>((size_t)chunk * E * P * P);
+        d_dds2 = bump.take<double>((size_t)chunk * E * P * P);
+        tmpA = bump.take<double>((size_t)chunk * E * P * P);
+        tmp_s2 = bump.take<double>((size_t)chunk * E);
+    }
+    double* d_Sigma = bump.take<double>((size_t)P * P);
+    GPD_CHECK(bump.off <= bump.cap, "internal: scratch overflow");
+    cudaStream_t s = c->stream;
+    GPD_CUDA(cudaMemcpyAsync(d_Sigma, Sigma, sizeof(double) * P * P, cudaMemcpyHostToDevice, s));
+    for (int64_t start = 0; start < N; start += chunk) {
+        const int nc = (int)std::min<int64_t>(chunk, N - start);
+        GPD_CUDA(cudaMemcpyAsync(d_mu, mu_io + (size_t)start * E, sizeof(double) * (size_t)nc * E, cudaMemcpyHostToDevice, s));
+        GPD_CUDA(cudaMemcpyAsync(d_s2, s2 + (size_t)start * E, sizeof(double) * (size_t)nc * E, cudaMemcpyHostToDevice, s));
+        GPD_CUDA(cudaMemcpyAsync(d_dmu, dmu + (size_t)start * E * P, sizeof(double) * (size_t)nc * E * P, cudaMemcpyHostToDevice, s));
+        if (order == 2) {
+            GPD_CUDA(cudaMemcpyAsync(d_ddmu, ddmu + (size_t)start * E * P * P, sizeof(double) * (size_t)nc * E * P * P,
+                                     cudaMemcpyHostToDevice, s));
+            GPD_CUDA(cudaMemcpyAsync(d_dds2, dds2 + (size_t)start * E * P * P, sizeof(double) * (size_t)nc * E * P * P,
+                                     cudaMemcpyHostToDevice, s));
+        }
+        {
+            Span sp(c, F_MARG, order == 2 ? 2 : 1, 0);
+            GPD_TRY(launch_assemble(s, order, nc, E, P, d_mu, E, d_s2, d_dmu, d_ddmu, d_dds2, d_Sigma, d_S, E * E, tmpA, tmp_s2));
+        }
+        if (order == 2)
+            GPD_CUDA(cudaMemcpyAsync(mu_io + (size_t)start * E, d_mu, sizeof(double) * (size_t)nc * E, cudaMemcpyDeviceToHost, s));
+        GPD_CUDA(cudaMemcpyAsync(S_out + (size_t)start * E * E, d_S, sizeof(double) * (size_t)nc * E * E, cudaMemcpyDeviceToHost, s));
+        GPD_CUDA(cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
+int gpd_criterion(gpd_ctx* c, int kind, const double* mu, const double* S, int64_t N, int32_t M, int32_t E,
+                  const double* noise, const double* pps, double* dc_out) {
+    GPD_CHECK(c && (N == 0 || (mu && S && noise && pps && dc_out)), "null argument");
+    GPD_CHECK(kind >= 0 && kind <= 4, "unknown criterion");
+    GPD_CHECK(M >= 1 && M <= 64, "number of models out of range (1..64)");
+    GPD_CHECK(E >= 1 && E <= kMaxE, "criteria support 1 <= E <= 8 outputs");
+    GPD_CUDA(cudaSetDevice(c->device));
+    if (N == 0) return 0;
+    const size_t per = sizeof(double) * ((size_t)M * E + (size_t)M * E * E + 1) + sizeof(double) * criterion_work_doubles(1, M, E);
+    int64_t chunk = std::min<int64_t>(N, std::max<int64_t>(1, (int64_t)((c->scratch_limit - (1 << 20)) / per)));
+    chunk = std::min<int64_t>(chunk, 1 << 24);
+    GPD_TRY(ensure_scratch(c, per * (size_t)chunk + (1 << 20)));
+    Bump bump(c->scratch.p, c->scratch.cap);
+    double* d_mu = bump.take<double>((size_t)chunk * M * E);
+    double* d_S = bump.take<double>((size_t)chunk * M * E * E);
+    double* d_dc = bump.take<double>((size_t)chunk);
+    double* d_work = bump.take<double>(criterion_work_doubles((int)chunk, M, E));
+    double* d_noise = bump.take<double>((size_t)E * E);
+    double* d_pps = bump.take<double>(M);
+    GPD_CHECK(bump.off <= bump.cap, "internal: scratch overflow");
+    cudaStream_t s = c->stream;
+    GPD_CUDA(cudaMemcpyAsync(d_noise, noise, sizeof(double) * E * E, cudaMemcpyHostToDevice, s));
+    GPD_CUDA(cudaMemcpyAsync(d_pps, pps, sizeof(double) * M, cudaMemcpyHostToDevice, s));
+    for (int64_t start = 0; start < N; start += chunk) {
+        const int nc = (int)std::min<int64_t>(chunk, N - start);
+        GPD_CUDA(cudaMemcpyAsync(d_mu, mu + (size_t)start * M * E, sizeof(double) * (size_t)nc * M * E, cudaMemcpyHostToDevice, s));
+        GPD_CUDA(cudaMemcpyAsync(d_S, S + (size_t)start * M * E * E, sizeof(double) * (size_t)nc * M * E * E,
+                                 cudaMemcpyHostToDevice, s));
+        {
+            Span sp(c, F_CRIT, 2, 0);
+            GPD_TRY(launch_criterion(s, kind, d_mu, d_S, nc, M, E, d_noise, d_pps, d_dc, d_work));
+        }
+        GPD_CUDA(cudaMemcpyAsync(dc_out + start, d_dc, sizeof(double) * nc, cudaMemcpyDeviceToHost, s));
+        GPD_CUDA(cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
+int gpd_argmax(gpd_ctx* c, const double* dc, int64_t N, double* best_val, int64_t* best_idx) {
+    GPD_CHECK(c && dc && best_val && best_idx, "null argument");
+    GPD_CHECK(N >= 1, "argmax of an empty sequence");
+    GPD_CUDA(cudaSetDevice(c->device));
+    const int64_t chunk = std::min<int64_t>(N, (int64_t)std::min<uint64_t>(c->scratch_limit, 1ull << 30) / 8);
+    GPD_TRY(ensure_scratch(c, (size_t)chunk * 8));
+    double* d = (double*)c->scratch.p;
+    cudaStream_t s = c->stream;
+    for (int64_t start = 0; start < N; start += chunk) {
+        const int64_t nc = std::min<int64_t>(chunk, N - start);
+        GPD_CUDA(cudaMemcpyAsync(d, dc + start, sizeof(double) * nc, cudaMemcpyHostToDevice, s));
+        Span sp(c, F_ARGMAX, 2, 0);
+        GPD_TRY(launch_argmax(s, d, nc, start, c->best_val_dev, c->best_idx_dev, start == 0, c->argmax_partial));
+    }
+    long long bi = -1;
+    GPD_CUDA(cudaMemcpyAsync(best_val, c->best_val_dev, sizeof(double), cudaMemcpyDeviceToHost, s));
+    GPD_CUDA(cudaMemcpyAsync(&bi, c->best_idx_dev, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    GPD_CUDA(cudaStreamSynchronize(s));
+    *best_idx = bi;
+    return 0;
+}
+
+// =================================================================================================
+// fused scoring
+// =================================================================================================
+static int score_impl(gpd_ctx* c, gpd_model* const* models, int32_t M, const double* X, bool x_on_device, int64_t N,
+                      int order, int kind, const double* noise, const double* pps, double* dc_out, bool dc_on_device,
+                      double* best_val, int64_t* best_idx, int64_t idx_offset) {
+    GPD_CHECK(c && models && X && noise && pps, "null argument");
+    GPD_CHECK(N >= 1, "no candidates");
+    GPD_CHECK(M >= 1 && M <= 64, "number of models out of range (1..64)");
+    GPD_CHECK(order == 1 || order == 2, "order must be 1 or 2");
+    GPD_CHECK(kind >= 0 && kind <= 4, "unknown criterion");
+    GPD_CUDA(cudaSetDevice(c->device));
+    const int E = models[0]->E, D = models[0]->D;
+    int maxP = 0;
+    for (int m = 0; m < M; ++m) {
+        GPD_CHECK(models[m] && models[m]->E == E && models[m]->D == D, "rival models must share num_outputs and dim_x");
+        GPD_CHECK(models[m]->has_sigma, "Sigma is not set on every model");
+        maxP = std::max(maxP, models[m]->P);
+    }
+    Plan pl;
+    size_t extra = sizeof(double) * ((size_t)M * E + (size_t)M * E * E + 1) + sizeof(double) * criterion_work_doubles(1, M, E);
+    if (!x_on_device) extra += sizeof(double) * D;
+    if (order == 2) extra += sizeof(double) * ((size_t)E * maxP * maxP + E);
+    GPD_TRY(plan_build(c, models, M, order_flags(order), N, extra, 0, pl));
+    const size_t total = pl.per_cand_bytes * ((size_t)pl.chunk + kBlk) + (8u << 20) + pl.entries.size() * sizeof(GpView) +
+                         (size_t)pl.entries.size() * pl.tiles * sizeof(Item);
+    GPD_TRY(ensure_scratch(c, total));
+    Bump bump(c->scratch.p, c->scratch.cap);
+    const int Nc = pl.chunk;
+    double* X_stage = x_on_device ? nullptr : bump.take<double>((size_t)Nc * D);
+    double* mu_all = bump.take<double>((size_t)Nc * M * E);
+    double* S_all = bump.take<double>((size_t)Nc * M * E * E);
+    double* dc_dev = bump.take<double>((size_t)Nc);
+    double* work = bump.take<double>(criterion_work_doubles(Nc, M, E));
+    double* tmpA = order == 2 ? bump.take<double>((size_t)Nc * E * maxP * maxP) : nullptr;
+    double* tmp_s2 = order == 2 ? bump.take<double>((size_t)Nc * E) : nullptr;
+    double* d_noise = bump.take<double>((size_t)E * E);
+    double* d_pps = bump.take<double>(M);
+    GPD_TRY(plan_materialize(c, pl, bump));
+    for (int m = 0; m < M; ++m) {   // finalize writes the means straight into the (N, M, E) criterion layout
+        pl.mb[m].mu = mu_all + (size_t)m * E;
+        pl.mb[m].ldmu = M * E;
+    }
+    cudaStream_t s = c->stream;
+    GPD_CUDA(cudaMemcpyAsync(d_noise, noise, sizeof(double) * E * E, cudaMemcpyHostToDevice, s));
+    GPD_CUDA(cudaMemcpyAsync(d_pps, pps, sizeof(double) * M, cudaMemcpyHostToDevice, s));
+    for (int64_t start = 0; start < N; start += Nc) {
+        const int nc = (int)std::min<int64_t>(Nc, N - start);
+        const double* Xc;
+        if (x_on_device) {
+            Xc = X + (size_t)start * D;
+        } else {
+            GPD_CUDA(cudaMemcpyAsync(X_stage, X + (size_t)start * D, sizeof(double) * (size_t)nc * D, cudaMemcpyHostToDevice, s));
+            Xc = X_stage;
+        }
+        GPD_TRY(run_chunk(c, pl, Xc, D, nc));
+        for (int m = 0; m < M; ++m) {
+            gpd_model* mo = models[m];
+            const ModelBufs& b = pl.mb[m];
+            const double* Sigma_dev = (const double*)((const char*)mo->xf_dev + offsetof(ModelXform, Sigma));
+            Span sp(c, F_MARG, order == 2 ? 2 : 1, 0);
+            GPD_TRY(launch_assemble(s, order, nc, E, mo->P, b.mu, b.ldmu, b.s2, b.dmu, b.d2mu, b.d2s2, Sigma_dev,
+                                    S_all + (size_t)m * E * E, M * E * E, tmpA, tmp_s2));
+        }
+        double* dc_target = (dc_out && dc_on_device) ? dc_out + start : dc_dev;
+        {
+            Span sp(c, F_CRIT, 2, 0);
+            GPD_TRY(launch_criterion(s, kind, mu_all, S_all, nc, M, E, d_noise, d_pps, dc_target, work));
+        }
+        {
+            Span sp(c, F_ARGMAX, 2, 0);
+            GPD_TRY(launch_argmax(s, dc_target, nc, idx_offset + start, c->best_val_dev, c->best_idx_dev, start == 0,
+                                  c->argmax_partial));
+        }
+        if (dc_out && !dc_on_device)
+            GPD_CUDA(cudaMemcpyAsync(dc_out + start, dc_dev, sizeof(double) * nc, cudaMemcpyDeviceToHost, s));
+    }
+    long long bi = -1;
+    double bv = 0;
+    GPD_CUDA(cudaMemcpyAsync(&bv, c->best_val_dev, sizeof(double), cudaMemcpyDeviceToHost, s));
+    GPD_CUDA(cudaMemcpyAsync(&bi, c->best_idx_dev, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    GPD_CUDA(cudaStreamSynchronize(s));
+    if (best_val) *best_val = bv;
+    if (best_idx) *best_idx = bi;
+    return 0;
+}
+
+int gpd_score(gpd_ctx* c, gpd_model* const* models, int32_t M, const double* X, int64_t N, int order, int kind,
+              const double* noise, const double* pps, double* dc_out, double* best_val, int64_t* best_idx,
+              int64_t idx_offset) {
+    return score_impl(c, models, M, X, false, N, order, kind, noise, pps, dc_out, false, best_val, best_idx, idx_offset);
+}
+int gpd_score_dev(gpd_ctx* c, gpd_model* const* models, int32_t M, const double* X_dev, int64_t N, int order, int kind,
+                  const double* noise, const double* pps, double* dc_out_dev, double* best_val, int64_t* best_idx,
+                  int64_t idx_offset) {
+    return score_impl(c, models, M, X_dev, true, N, order, kind, noise, pps, dc_out_dev, true, best_val, best_idx, idx_offset);
+}
+
+// ---- layout self-description --------------------------------------------------------------------
+int32_t gpd_layout_a_index(int32_t ms, int32_t ks, int32_t lane) { return a_index(ms, ks, lane); }
+int32_t gpd_layout_a_row(int32_t ms, int32_t lane) { return a_row(ms, lane); }
+int32_t gpd_layout_a_col(int32_t ks, int32_t lane) { return a_col(ks, lane); }
+int32_t gpd_layout_b_index(int32_t k, int32_t t) { return b_index(k, t); }
+int64_t gpd_layout_tile_offset(int32_t nblk, int32_t I, int32_t kb, int32_t backward) {
+    const int kfirst = tile_run_kfirst(I, backward);
+    const int len = tile_run_len(nblk, I, backward);
+    if (kb < kfirst || kb >= kfirst + len) return -1;
+    return (tile_run_base(nblk, I, backward) + (kb - kfirst)) * (long long)kTileElems;
+}
+int32_t gpd_binary_combo_weight(int32_t n_binary, int32_t v) { return binary_combo_weight(n_binary, v); }
+
+}  // extern "C"

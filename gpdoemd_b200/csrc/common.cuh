@@ -1,0 +1,121 @@
+// Internal declarations shared by the translation units of libgpdoemd_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "layout.h"
+
+namespace gpd {
+
+constexpr int kMaxXDims = 8;     // active (non-binary) design dimensions handled by the evaluation kernel
+constexpr int kMaxP = 16;        // model parameters
+constexpr int kMaxE = 8;         // outputs (register-resident E x E criteria)
+constexpr int kMaxBinary = 6;
+
+// Device-side view of one GP (array in global memory, indexed by work items).
+struct GpView {
+    int kernel, n, n_pad, nblk, nx, P;
+    double kss;                  // var_x * var_p = k(z*, z*)
+    double power_x;
+    const double* Xs;            // [n_pad][nx]  training x / lengthscale   (pad rows 0)
+    const double* C;             // [1+P+P(P+1)/2][n_pad] alpha*var_x*{kp, dkp/dp_a, d2kp/dp_a dp_b (a<=b)}
+    const double* G;             // [1+P][n_pad]          var_x*{kp, dkp/dp_a}          (pad rows 0)
+    const double* H;             // [P(P+1)/2][n_pad]     var_x*d2kp/dp_a dp_b
+    const double* LinvF;         // packed forward factor  (layout.h)
+    const double* LinvB;         // packed backward factor
+    double ls[kMaxXDims];        // x lengthscales of the active dims
+    double xmin[kMaxXDims], xdiff[kMaxXDims];
+    int x_active[kMaxXDims];
+    // routing of this GP inside the current chunk
+    const int* idx;              // candidate positions (within chunk) handled by this GP, or null = identity
+    const int* count;            // device count of those positions, or null = chunk size
+    int out_e;                   // output row e of the owning model
+    int model;                   // model slot inside the current call
+    long long panel_off;         // offset of this GP's panel region, in doubles per RHS kind
+};
+
+// Work item of the evaluation / triangular kernels: GP + candidate tile (128 columns).
+struct Item { int gp; int tile; };
+
+// Per-model raw outputs for a chunk (device pointers), transformed units.
+struct RawOut {
+    double* cmu;    // [E][Nc][ldraw]  kx . C columns
+    double* kss;    // [E][Nc]         k** of the GP that handled the row (0 = unrouted)
+    double* gram;   // [E][Nc][ng]     ng = 1 (v'v) or (1+P)(2+P)/2 upper triangle of [v W]'[v W]
+    double* bh;     // [E][Nc][P(P+1)/2]   beta . (kx * d2kp)
+};
+
+struct ModelXform {              // device copy of the per-model unit conversions
+    int E, P;
+    double ymean[kMaxE], ystd[kMaxE];
+    double pdiff[kMaxP];
+    double Sigma[kMaxP * kMaxP]; // row-major, stride P
+};
+
+void set_error(const std::string& msg);
+#define GPD_CUDA(call)                                                                        \
+    do {                                                                                      \
+        cudaError_t err__ = (call);                                                           \
+        if (err__ != cudaSuccess) {                                                           \
+            ::gpd::set_error(std::string(#call) + ": " + cudaGetErrorString(err__) + " (" +   \
+                             __FILE__ + ":" + std::to_string(__LINE__) + ")");                \
+            return 1;                                                                         \
+        }                                                                                     \
+    } while (0)
+#define GPD_CHECK(cond, msg)                                                                  \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            ::gpd::set_error(std::string(msg) + " [" #cond "] (" + __FILE__ + ":" +          \
+                             std::to_string(__LINE__) + ")");                                 \
+            return 2;                                                                         \
+        }                                                                                     \
+    } while (0)
+#define GPD_TRY(expr)                                                                         \
+    do {                                                                                      \
+        int rc__ = (expr);                                                                    \
+        if (rc__) return rc__;                                                                \
+    } while (0)
+
+// ---- kernel launchers (0 = ok) ----------------------------------------------------------------
+// kernels_eval.cu
+int launch_pstate(cudaStream_t s, int kernel, int n, int n_pad, int P, int dim_z, const double* Zp,
+                  const double* alpha, const double* pstar, const double* ls_p, double var_x, double var_p,
+                  double power_p, double* C, double* G, double* H);
+int launch_eval(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int nitems, const double* X_dev,
+                int ldx, int chunk_n, int nrhs, int ncols, int kernel, int nx, double* panels,
+                const RawOut* raw_dev, int ldraw);
+int launch_beta_contract(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int nitems,
+                         const double* X_dev, int ldx, int chunk_n, int kernel, int nx, int P,
+                         const double* beta_panels, const RawOut* raw_dev);
+// kernels_tri.cu
+int launch_invert_and_pack(cudaStream_t s, const double* L_dev, int n, int n_pad, double* dense_tmp,
+                           double* packF, double* packB, uint64_t* launches);
+int launch_tri(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int nitems, int nwork_rhs,
+               int in_stride, int out_stride, int backward, const double* panels_in, double* panels_out,
+               const RawOut* raw_dev, int ng, int chunk_n, int num_sms, int variant);
+int launch_gram(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int nitems, int nrhs,
+                const double* panels, const RawOut* raw_dev, int chunk_n);
+int launch_dmma_probe(cudaStream_t s, int num_sms, int iters, double* sink_dev);
+// kernels_crit.cu
+int launch_route(cudaStream_t s, const double* X_dev, int ldx, int chunk_n, int nb, const int* bcols,
+                 const int* weights, int ncombo, int* idx, int* counts, int idx_stride);
+int launch_finalize(cudaStream_t s, const ModelXform* xf_dev, const RawOut* raw_dev, int model_slot, int E, int P,
+                    int chunk_n, int ldraw, int flags, int nrhs, double* mu, int ldmu, double* s2, double* dmu,
+                    double* d2mu, double* ds2, double* d2s2);
+int launch_assemble(cudaStream_t s, int order, int N, int E, int P, double* mu, int ldmu, const double* s2,
+                    const double* dmu, const double* d2mu, const double* d2s2, const double* Sigma_dev, double* S,
+                    int ldS, double* tmpA, double* tmp_s2);
+int launch_criterion(cudaStream_t s, int kind, const double* mu, const double* S, int N, int M, int E,
+                     const double* noise_dev, const double* pps_dev, double* dc, double* work);
+size_t criterion_work_doubles(int N, int M, int E);
+int launch_argmax(cudaStream_t s, const double* dc, long long N, long long idx_base, double* best_val_dev,
+                  long long* best_idx_dev, int first, void* partial_dev);
+size_t argmax_partial_bytes();
+int launch_fill_uniform(cudaStream_t s, double* X, long long N, int D, uint64_t seed, long long first_row,
+                        const double* lo_dev, const double* hi_dev);
+int launch_flush(cudaStream_t s, double* buf, size_t n);
+
+}  // namespace gpd

@@ -1,0 +1,520 @@
+// K2: the triangular contraction  V = L^-1 K*  (and  beta = L^-T v) on the FP64 tensor pipe.
+//
+// Reference arithmetic: GPy PosteriorExact._raw_predict  `tmp = dtrtrs(woodbury_chol, Kx)` reached from
+// GPdoemd/models/gp_model.py:199, and the `woodbury_inv` products of gp_model.py:263-274.
+//
+// B200 design.  f64 has no tcgen05/TMEM kind, so the tensor path is mma.sync m8n8k4 (SASS DMMA.8x8x4)
+// with accumulators in registers.  The solve against the cached Cholesky factor is tiled as a GEMM by
+// pre-inverting the factor ONCE per GP on the device (blocked forward substitution on the identity) and
+// packing it into tensor-core fragment order (layout.h).  Per candidate tile the kernel then streams
+// 16 KiB A chunks (packed L^-1, L2 resident, shared by all CTAs) and 16 KiB B chunks (kernel rows of
+// 128 candidates) with 1-D bulk async copies (cp.async.bulk -> SASS UBLKCP) into a 4-stage mbarrier
+// ring; one producer warp issues copies, 16 (or 8) consumer warps issue DMMA.  Row blocks of the
+// triangular product are independent, so there is no serial dependency and nothing but ||v||^2 leaves the
+// SM on the first-order path.  Zero sub-blocks of the diagonal tiles are skipped at 8-row granularity.
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace gpd {
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void consumer_bar(int nthreads) {
+    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// the persistent triangular-GEMM kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int kStages = 4;
+constexpr uint32_t kChunkBytes = kChunkElems * sizeof(double);   // 16384
+
+struct TriSmem {
+    double A[kStages][kChunkElems];
+    double B[kStages][kChunkElems];
+    double colsum[4][kBlk];
+    unsigned long long full[kStages];
+    unsigned long long empty[kStages];
+};
+
+struct TriArgs {
+    const GpView* gps;
+    const Item* items;
+    int nitems;
+    int nwork_rhs;        // RHS kinds processed per item (a = 0 .. nwork_rhs-1)
+    int in_stride;        // RHS kinds per tile in the input panel buffer
+    int out_stride;       // RHS kinds per tile in the output panel buffer
+    int backward;         // 0: V = Linv * R ; 1: beta = Linv^T * V
+    const double* panels_in;
+    double* panels_out;   // may be null
+    const RawOut* raws;   // non-null: write column sums of squares into raw.gram[..][0]
+    int ng;               // row length of raw.gram
+    int chunk_n;
+};
+
+template <int WM, int WN, bool DIAG>
+__device__ __forceinline__ void compute_chunk(const double* __restrict__ sA, const double* __restrict__ sB, int lane,
+                                              int wm, int wn, int chunk_in_blk, int backward,
+                                              double (&acc)[16 / WM][16 / WN][2]) {
+    constexpr int MB = 16 / WM, NB = 16 / WN;
+    const int lq = lane & 3, lr = lane >> 2;
+#pragma unroll
+    for (int kp = 0; kp < 2; ++kp) {
+        double2 a2[MB];
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb)
+            a2[mb] = *reinterpret_cast<const double2*>(sA + a_index(wm * MB + mb, kp * 2, lane));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int ks = kp * 2 + h;
+            double b[NB];
+            const int krow = ks * 4 + lq;
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) b[nb] = sB[b_index(krow, (wn * NB + nb) * 8 + lr)];
+            const int k0 = chunk_in_blk * kChunkK + ks * 4;     // first k of this k4 step inside the 128 block
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+                if (DIAG) {
+                    const int r = (wm * MB + mb) * 8;           // first row of this 8-row block
+                    // forward (lower): entries with k <= row ; backward (upper): entries with k >= row
+                    const bool zero = backward ? (k0 + 3 < r) : (k0 > r + 7);
+                    if (zero) continue;
+                }
+                const double a = h ? a2[mb].y : a2[mb].x;
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a, b[nb]);
+            }
+        }
+    }
+}
+
+template <int WM, int WN>
+__global__ void __launch_bounds__((WM * WN + 1) * 32, 1) tri_kernel(const TriArgs args) {
+    constexpr int NCW = WM * WN;            // consumer warps
+    constexpr int MB = 16 / WM, NB = 16 / WN;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TriSmem& sm = *reinterpret_cast<TriSmem*>(smem_raw);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(smem_u32(&sm.full[s]), 1);
+            mbar_init(smem_u32(&sm.empty[s]), NCW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int k = threadIdx.x; k < 4 * kBlk; k += blockDim.x) (&sm.colsum[0][0])[k] = 0.0;
+    __syncthreads();
+
+    const int nwork = args.nitems * args.nwork_rhs;
+    int stage = 0;
+    uint32_t phase = 0;
+
+    if (warp == NCW) {
+        // ===== producer: one lane streams A (packed factor) and B (RHS panel) chunks =====
+        if (lane != 0) return;
+        for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+            const Item it = args.items[w / args.nwork_rhs];
+            const int a = w % args.nwork_rhs;
+            const GpView& g = args.gps[it.gp];
+            const int count = g.count ? *g.count : args.chunk_n;
+            if (it.tile * kBlk >= count) continue;
+            const int nblk = g.nblk, n_pad = g.n_pad;
+            const double* pack = args.backward ? g.LinvB : g.LinvF;
+            const double* Bsrc = args.panels_in + g.panel_off * args.in_stride +
+                                 ((size_t)(it.tile * args.in_stride + a) * n_pad) * kBlk;
+            for (int I = 0; I < nblk; ++I) {
+                const double* Arun = pack + tile_run_base(nblk, I, args.backward) * (long long)kTileElems;
+                const int len = tile_run_len(nblk, I, args.backward);
+                const int kfirst = tile_run_kfirst(I, args.backward);
+                for (int q = 0; q < len; ++q) {
+                    const double* At = Arun + (size_t)q * kTileElems;
+                    const double* Bt = Bsrc + (size_t)(kfirst + q) * kBlk * kBlk;
+                    for (int c = 0; c < kChunksPerBlk; ++c) {
+                        mbar_wait(smem_u32(&sm.empty[stage]), phase ^ 1);
+                        const uint32_t fb = smem_u32(&sm.full[stage]);
+                        mbar_expect_tx(fb, 2 * kChunkBytes);
+                        bulk_g2s(smem_u32(sm.A[stage]), At + (size_t)c * kChunkElems, kChunkBytes, fb);
+                        bulk_g2s(smem_u32(sm.B[stage]), Bt + (size_t)c * kChunkElems, kChunkBytes, fb);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers: DMMA over the chunk stream =====
+    const int wm = warp / WN, wn = warp % WN;       // warp w lives on SMSP w%4: every SMSP sees all row groups
+    const int lq = lane & 3, lr = lane >> 2;
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const Item it = args.items[w / args.nwork_rhs];
+        const int a = w % args.nwork_rhs;
+        const GpView& g = args.gps[it.gp];
+        const int count = g.count ? *g.count : args.chunk_n;
+        if (it.tile * kBlk >= count) continue;
+        const int nblk = g.nblk, n_pad = g.n_pad;
+        double* Out = args.panels_out
+                          ? args.panels_out + g.panel_off * args.out_stride +
+                                ((size_t)(it.tile * args.out_stride + a) * n_pad) * kBlk
+                          : nullptr;
+        double csq[NB][2];
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) csq[nb][0] = csq[nb][1] = 0.0;
+
+        for (int I = 0; I < nblk; ++I) {
+            double acc[MB][NB][2];
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+            const int len = tile_run_len(nblk, I, args.backward);
+            const int qdiag = args.backward ? 0 : len - 1;
+            for (int q = 0; q < len; ++q) {
+                const bool diag = (q == qdiag);
+                for (int c = 0; c < kChunksPerBlk; ++c) {
+                    mbar_wait(smem_u32(&sm.full[stage]), phase);
+                    if (diag)
+                        compute_chunk<WM, WN, true>(sm.A[stage], sm.B[stage], lane, wm, wn, c, args.backward, acc);
+                    else
+                        compute_chunk<WM, WN, false>(sm.A[stage], sm.B[stage], lane, wm, wn, c, args.backward, acc);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stage]));
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+            // ---- epilogue of row block I: optional store of V, running column sums of squares ----
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+                const int i = I * kBlk + (wm * MB + mb) * 8 + lr;
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    const double v0 = acc[mb][nb][0], v1 = acc[mb][nb][1];
+                    csq[nb][0] = fma(v0, v0, csq[nb][0]);
+                    csq[nb][1] = fma(v1, v1, csq[nb][1]);
+                    if (Out) {
+                        const int t0 = (wn * NB + nb) * 8 + 2 * lq;
+                        *reinterpret_cast<double2*>(Out + (size_t)i * kBlk + (t0 ^ ((i & 3) << 2))) =
+                            make_double2(v0, v1);
+                    }
+                }
+            }
+        }
+        if (args.raws) {
+            // reduce over the 8 lanes that own the same columns (lane bits 2..4), then over row groups
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    double s = csq[nb][j];
+                    s += __shfl_xor_sync(0xffffffffu, s, 4);
+                    s += __shfl_xor_sync(0xffffffffu, s, 8);
+                    s += __shfl_xor_sync(0xffffffffu, s, 16);
+                    if (lr == 0) sm.colsum[wm][(wn * NB + nb) * 8 + 2 * lq + j] = s;
+                }
+            consumer_bar(NCW * 32);
+            if (threadIdx.x < kBlk) {
+                const int t = threadIdx.x;
+                double tot = 0.0;
+#pragma unroll
+                for (int r = 0; r < WM; ++r) tot += sm.colsum[r][t];
+                const int slot = it.tile * kBlk + t;
+                if (slot < count) {
+                    const int cand = g.idx ? g.idx[slot] : slot;
+                    const RawOut& raw = args.raws[g.model];
+                    raw.gram[((size_t)g.out_e * args.chunk_n + cand) * args.ng] = tot;
+                }
+            }
+            consumer_bar(NCW * 32);
+        }
+    }
+}
+
+static bool g_tri_attr_done = false;
+int tri_setup_attributes() {
+    if (g_tri_attr_done) return 0;
+    GPD_CUDA(cudaFuncSetAttribute(tri_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TriSmem)));
+    GPD_CUDA(cudaFuncSetAttribute(tri_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TriSmem)));
+    g_tri_attr_done = true;
+    return 0;
+}
+
+int launch_tri(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int nitems, int nwork_rhs,
+               int in_stride, int out_stride, int backward, const double* panels_in, double* panels_out,
+               const RawOut* raw_dev, int ng, int chunk_n, int num_sms, int variant) {
+    if (nitems == 0) return 0;
+    GPD_TRY(tri_setup_attributes());
+    TriArgs args;
+    args.gps = gps_dev;
+    args.items = items_dev;
+    args.nitems = nitems;
+    args.nwork_rhs = nwork_rhs;
+    args.in_stride = in_stride;
+    args.out_stride = out_stride;
+    args.backward = backward;
+    args.panels_in = panels_in;
+    args.panels_out = panels_out;
+    args.raws = raw_dev;
+    args.ng = ng;
+    args.chunk_n = chunk_n;
+    long long nwork = (long long)nitems * nwork_rhs;
+    int grid = (int)(nwork < num_sms ? nwork : num_sms);
+    if (variant == 1)
+        tri_kernel<2, 4><<<grid, (2 * 4 + 1) * 32, sizeof(TriSmem), s>>>(args);
+    else
+        tri_kernel<4, 4><<<grid, (4 * 4 + 1) * 32, sizeof(TriSmem), s>>>(args);
+    GPD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gram kernel (second order / d_s2_d_p): upper triangle of [v W]^T [v W] per candidate
+// ---------------------------------------------------------------------------------------------
+template <int NR>
+__global__ void __launch_bounds__(2 * kBlk) gram_kernel(const GpView* __restrict__ gps, const Item* __restrict__ items,
+                                                        const double* __restrict__ panels,
+                                                        const RawOut* __restrict__ raws, int chunk_n) {
+    constexpr int NG = NR * (NR + 1) / 2;
+    extern __shared__ double red[];            // [NG][kBlk]
+    const Item it = items[blockIdx.x];
+    const GpView& g = gps[it.gp];
+    const int count = g.count ? *g.count : chunk_n;
+    if (it.tile * kBlk >= count) return;
+    const int t = threadIdx.x & (kBlk - 1), rg = threadIdx.x >> 7;
+    const int n_pad = g.n_pad;
+    const double* base = panels + g.panel_off * NR + ((size_t)it.tile * NR * n_pad) * kBlk;
+    double acc[NG];
+#pragma unroll
+    for (int k = 0; k < NG; ++k) acc[k] = 0.0;
+    for (int i = rg; i < n_pad; i += 2) {
+        const int pos = t ^ ((i & 3) << 2);
+        double v[NR];
+#pragma unroll
+        for (int a = 0; a < NR; ++a) v[a] = base[((size_t)a * n_pad + i) * kBlk + pos];
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < NR; ++a)
+#pragma unroll
+            for (int b = a; b < NR; ++b, ++k) acc[k] = fma(v[a], v[b], acc[k]);
+    }
+    if (rg == 1) {
+#pragma unroll
+        for (int k = 0; k < NG; ++k) red[k * kBlk + t] = acc[k];
+    }
+    __syncthreads();
+    if (rg == 0) {
+        const int slot = it.tile * kBlk + t;
+        if (slot < count) {
+            const int cand = g.idx ? g.idx[slot] : slot;
+            const RawOut& raw = raws[g.model];
+            double* out = raw.gram + ((size_t)g.out_e * chunk_n + cand) * NG;
+#pragma unroll
+            for (int k = 0; k < NG; ++k) out[k] = acc[k] + red[k * kBlk + t];
+        }
+    }
+}
+
+int launch_gram(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int nitems, int nrhs,
+                const double* panels, const RawOut* raw_dev, int chunk_n) {
+    if (nitems == 0) return 0;
+#define GPD_GRAM_CASE(NRV)                                                                              \
+    case NRV: {                                                                                         \
+        const int smem = NRV * (NRV + 1) / 2 * kBlk * (int)sizeof(double);                              \
+        GPD_CUDA(cudaFuncSetAttribute(gram_kernel<NRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        gram_kernel<NRV><<<nitems, 2 * kBlk, smem, s>>>(gps_dev, items_dev, panels, raw_dev, chunk_n);  \
+    } break;
+    switch (nrhs) {
+        GPD_GRAM_CASE(2)
+        GPD_GRAM_CASE(3)
+        GPD_GRAM_CASE(4)
+        GPD_GRAM_CASE(5)
+        GPD_GRAM_CASE(6)
+        GPD_GRAM_CASE(7)
+        GPD_GRAM_CASE(8)
+        GPD_GRAM_CASE(9)
+        GPD_GRAM_CASE(10)
+        GPD_GRAM_CASE(11)
+        default:
+            set_error("variance-derivative path supports 1 <= P <= 10 model parameters");
+            return 3;
+    }
+#undef GPD_GRAM_CASE
+    GPD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one-time per GP: X = L^-1 by blocked forward substitution on the identity, then packing
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double L_at(const double* __restrict__ L, int n, int i, int k) {
+    // padded factor: identity outside the n x n lower triangle
+    if (i < n && k < n) return (k <= i) ? L[(size_t)i * n + k] : 0.0;
+    return (i == k) ? 1.0 : 0.0;
+}
+
+// D_J = inv(L_JJ): thread c solves L_JJ x = e_c ; X is the dense n_pad x n_pad result (zero initialised)
+__global__ void __launch_bounds__(kBlk) diag_inv_kernel(const double* __restrict__ L, int n, int n_pad,
+                                                        double* __restrict__ X) {
+    const int J = blockIdx.x, c = threadIdx.x;
+    const int r0 = J * kBlk;
+    double x[kBlk];
+    for (int i = 0; i < kBlk; ++i) {
+        double s = (i == c) ? 1.0 : 0.0;
+        if (i >= c) {
+            for (int m = c; m < i; ++m) s = fma(-L_at(L, n, r0 + i, r0 + m), x[m], s);
+            s = s / L_at(L, n, r0 + i, r0 + i);
+        } else {
+            s = 0.0;
+        }
+        x[i] = s;
+        if (i >= c) X[(size_t)(r0 + i) * n_pad + r0 + c] = s;
+    }
+}
+
+// X_JK = -D_J * sum_{m=K}^{J-1} L_Jm X_mK   for one block row J; CTA = (K, 32-column slab)
+__global__ void __launch_bounds__(256) offdiag_kernel(const double* __restrict__ L, int n, int n_pad, int J,
+                                                      double* __restrict__ X) {
+    __shared__ double T[kBlk][33];
+    const int K = blockIdx.x, slab = blockIdx.y;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // ty: 16 rows each
+    const int col = K * kBlk + slab * 32 + tx;
+    const int r0 = J * kBlk;
+    double acc[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc[r] = 0.0;
+    // columns of X_mK below the diagonal of block K are zero for rows < col: start at the slab's first column
+    const int kbeg = K * kBlk + slab * 32, kend = J * kBlk;
+    for (int k = kbeg; k < kend; ++k) {
+        const double xv = X[(size_t)k * n_pad + col];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) acc[r] = fma(L_at(L, n, r0 + ty * 16 + r, k), xv, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) T[ty * 16 + r][tx] = acc[r];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc[r] = 0.0;
+    const int imax = ty * 16 + 15;
+    for (int m = 0; m <= imax; ++m) {
+        const double tv = T[m][tx];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int i = ty * 16 + r;
+            if (m <= i) acc[r] = fma(X[(size_t)(r0 + i) * n_pad + r0 + m], tv, acc[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) X[(size_t)(r0 + ty * 16 + r) * n_pad + col] = -acc[r];
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(const double* __restrict__ X, int n_pad, int nblk, int backward,
+                                                   double* __restrict__ out) {
+    // blockIdx.x = packed tile index; find (I, q)
+    const long long tile = blockIdx.x;
+    int I = 0;
+    while (I + 1 < nblk && tile_run_base(nblk, I + 1, backward) <= tile) ++I;
+    const int q = (int)(tile - tile_run_base(nblk, I, backward));
+    const int kb = tile_run_kfirst(I, backward) + q;
+    double* dst = out + tile * (long long)kTileElems;
+    for (int e = threadIdx.x; e < kTileElems; e += blockDim.x) {
+        const int c = e / kChunkElems, idx = e % kChunkElems;
+        const int h = idx & 1, lane = (idx >> 1) & 31, msk = idx >> 6;
+        const int kp = msk & 1, ms = msk >> 1;
+        const int ks = kp * 2 + h;
+        const int row = I * kBlk + a_row(ms, lane);
+        const int col = kb * kBlk + c * kChunkK + a_col(ks, lane);
+        dst[e] = backward ? X[(size_t)col * n_pad + row] : X[(size_t)row * n_pad + col];
+    }
+}
+
+int launch_invert_and_pack(cudaStream_t s, const double* L_dev, int n, int n_pad, double* dense_tmp, double* packF,
+                           double* packB, uint64_t* launches) {
+    const int nblk = n_pad / kBlk;
+    GPD_CUDA(cudaMemsetAsync(dense_tmp, 0, sizeof(double) * (size_t)n_pad * n_pad, s));
+    diag_inv_kernel<<<nblk, kBlk, 0, s>>>(L_dev, n, n_pad, dense_tmp);
+    GPD_CUDA(cudaGetLastError());
+    *launches += 1;
+    for (int J = 1; J < nblk; ++J) {
+        offdiag_kernel<<<dim3(J, 4), 256, 0, s>>>(L_dev, n, n_pad, J, dense_tmp);
+        GPD_CUDA(cudaGetLastError());
+        *launches += 1;
+    }
+    const int ntiles = (int)packed_tiles(nblk);
+    if (packF) {
+        pack_kernel<<<ntiles, 256, 0, s>>>(dense_tmp, n_pad, nblk, 0, packF);
+        GPD_CUDA(cudaGetLastError());
+        *launches += 1;
+    }
+    if (packB) {
+        pack_kernel<<<ntiles, 256, 0, s>>>(dense_tmp, n_pad, nblk, 1, packB);
+        GPD_CUDA(cudaGetLastError());
+        *launches += 1;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// register-resident DMMA peak probe (roofline denominator measured in the same process as the bench)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dmma_probe_kernel(double* out, int iters, double a, double b) {
+    constexpr int CH = 8;
+    double c0[CH], c1[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        c0[i] = threadIdx.x * 1e-9 + i;
+        c1[i] = i;
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) dmma884(c0[i], c1[i], a, b);
+    }
+    double sacc = 0;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) sacc += c0[i] + c1[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = sacc;
+}
+
+int launch_dmma_probe(cudaStream_t s, int num_sms, int iters, double* sink_dev) {
+    dmma_probe_kernel<<<num_sms * 2, 256, 0, s>>>(sink_dev, iters, 1.0000001, 1e-9);
+    GPD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace gpd

@@ -1,0 +1,118 @@
+"""Fused design scoring: the loop of ``demos/case_study.py:279-293`` in one device pass.
+
+``score_designs(models, X, order, criterion, noise_var, pps)`` is equivalent to
+
+    for i, M in enumerate(models): mu[:, i], s2[:, i] = taylor_{first,second}_order(M, X)
+    dc = CRITERION(mu, s2, noise_var, pps);  best = np.argmax(dc)
+
+with nothing N-sized leaving the GPU unless ``return_dc`` is set.  ``ShardedScorer`` splits the candidates
+over the ranks of a ``torch.distributed`` process group (one process per GPU, GP factors replicated,
+contiguous blocks) and combines the per-rank (max, index) pairs with one all-gather; ties go to the
+lowest global index, like ``np.argmax`` on the unsharded vector.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, dptr
+from .context import get_context
+from .design_criteria import _reshape
+
+
+def _prep(models, criterion, noise_var, pps):
+    M, E = len(models), models[0].num_outputs
+    _, _, noise, pps_n, _, _, _ = _reshape(np.zeros((1, M, E)), np.zeros((1, M, E, E)), noise_var, pps)
+    handles = (C.c_void_p * M)(*[m.device_handle() for m in models])
+    return _lib.CRITERION_IDS[criterion], _lib.as_f64(noise), _lib.as_f64(pps_n), handles
+
+
+def score_designs(models, X, order=1, criterion='BH', noise_var=None, pps=None, return_dc=True, idx_offset=0):
+    """-> (best_index, best_value, dc or None).  X: (N, dim_x) host array in original units."""
+    X = _lib.as_f64(X)
+    N = len(X)
+    dev = models[0]._device
+    ctx = get_context(dev)
+    kind, noise, pps_n, handles = _prep(models, criterion, noise_var, pps)
+    dc = np.empty(N) if return_dc else None
+    bv, bi = C.c_double(), C.c_int64()
+    check(ctx.lib.gpd_score(ctx.handle, C.cast(handles, _lib.c_void_pp), len(models), dptr(X), N, order, kind,
+                            dptr(noise), dptr(pps_n), dptr(dc), C.byref(bv), C.byref(bi), int(idx_offset)))
+    return int(bi.value), bv.value, dc
+
+
+def score_designs_dev(models, X_dev, N, order=1, criterion='BH', noise_var=None, pps=None, dc_dev=None,
+                      idx_offset=0):
+    """Same with candidates (and optionally the criterion vector) resident in device memory."""
+    dev = models[0]._device
+    ctx = get_context(dev)
+    kind, noise, pps_n, handles = _prep(models, criterion, noise_var, pps)
+    bv, bi = C.c_double(), C.c_int64()
+    check(ctx.lib.gpd_score_dev(ctx.handle, C.cast(handles, _lib.c_void_pp), len(models), X_dev, int(N), order, kind,
+                                dptr(noise), dptr(pps_n), dc_dev, C.byref(bv), C.byref(bi), int(idx_offset)))
+    return int(bi.value), bv.value
+
+
+def shard_bounds(N, rank, world):
+    """Contiguous block [lo, hi) of rank: ceil(N/world) candidates each."""
+    per = -(-N // world)
+    lo = min(N, rank * per)
+    return lo, min(N, lo + per)
+
+
+def combine_best(vals, idxs):
+    """np.argmax semantics over per-shard winners: NaN wins, ties -> lowest global index."""
+    best = None
+    for v, i in zip(vals, idxs):
+        if i < 0:
+            continue
+        if best is None:
+            best = (v, i)
+            continue
+        bv, bi = best
+        nv, nb = np.isnan(v), np.isnan(bv)
+        if nv or nb:
+            better = nv and (not nb or i < bi)
+        else:
+            better = v > bv or (v == bv and i < bi)
+        if better:
+            best = (v, i)
+    return best
+
+
+class ShardedScorer:
+    """Data-parallel scoring over a torch.distributed group (NCCL on GPUs, gloo in CPU tests).
+
+    ``local_score(lo, hi) -> (best_value, best_global_index)`` is the per-rank work; the only
+    collective is an all-gather of one (float64, int64) pair per rank.
+    """
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def argmax_allgather(self, best_val, best_idx, device=None):
+        import torch
+        dist = self.dist
+        backend = dist.get_backend(self.group)
+        dev = device if device is not None else ('cuda' if backend == 'nccl' else 'cpu')
+        v = torch.tensor([best_val], dtype=torch.float64, device=dev)
+        i = torch.tensor([best_idx], dtype=torch.int64, device=dev)
+        vs = [torch.empty_like(v) for _ in range(self.world)]
+        is_ = [torch.empty_like(i) for _ in range(self.world)]
+        dist.all_gather(vs, v, group=self.group)
+        dist.all_gather(is_, i, group=self.group)
+        vals = [float(t.item()) for t in vs]
+        idxs = [int(t.item()) for t in is_]
+        return combine_best(vals, idxs)
+
+    def score(self, N, local_score):
+        lo, hi = shard_bounds(N, self.rank, self.world)
+        if hi > lo:
+            v, i = local_score(lo, hi)
+        else:
+            v, i = 0.0, -1
+        return self.argmax_allgather(v, i)

@@ -1,0 +1,25 @@
+"""Shared builders for the parity tests: the SAME training data, hyper-parameters, alpha and Cholesky
+factor go to the oracle (CPU) and to the CUDA path (gpdoemd_b200.GPModel.from_reference)."""
+import numpy as np
+
+from gpdoemd_b200 import synthetic
+from oracle import gpy_kernels
+from oracle.model import OracleGPModel
+
+
+def oracle_models(seed, M, E, D, P, n, kernel, n_binary=0):
+    return synthetic.build_models(OracleGPModel, seed, M, E, D, P, n, kernel, n_binary,
+                                  kernel_lookup=gpy_kernels.KERNELS)
+
+
+def gpu_models(oracle_ms):
+    from gpdoemd_b200 import GPModel
+    return [GPModel.from_reference(m) for m in oracle_ms]
+
+
+def relerr(a, b, scale=None):
+    """max |a-b| / max(|b|, scale): relative error with a floor at the quantity's natural scale."""
+    a, b = np.asarray(a), np.asarray(b)
+    den = np.abs(b) if scale is None else np.maximum(np.abs(b), scale)
+    den = np.where(den == 0, 1.0, den)
+    return float(np.max(np.abs(a - b) / den))
