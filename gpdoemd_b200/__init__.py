@@ -5,14 +5,14 @@ FP64 CUDA for sm_100a behind the reference's Python classes and function signatu
 package does not need a GPU; the first call that computes anything does, and raises if the CUDA library
 or device is missing (there is no CPU fallback).
 """
-from . import design_criteria, kernels, marginal, scoring
+from . import design_criteria, kernels, marginal, scoring, synthetic
 from .context import Context, get_context
 from .design_criteria import AW, BF, BH, HR, JR
 from .gp_state import ExactGP, GPState
 from .marginal import taylor_first_order, taylor_second_order
 from .models import GPModel
-from .scoring import ShardedScorer, score_designs, score_designs_dev
+from .scoring import ShardedScorer, score_designs, score_designs_dev, score_designs_multi
 
 __all__ = ['GPModel', 'GPState', 'ExactGP', 'Context', 'get_context', 'kernels', 'marginal', 'design_criteria',
            'scoring', 'taylor_first_order', 'taylor_second_order', 'HR', 'BH', 'BF', 'AW', 'JR', 'score_designs',
-           'score_designs_dev', 'ShardedScorer']
+           'score_designs_dev', 'score_designs_multi', 'ShardedScorer', 'synthetic']

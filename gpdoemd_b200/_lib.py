@@ -68,6 +68,9 @@ _SIGNATURES = {
                             c_double_p, c_double_p, c_double_p, C.POINTER(C.c_int64), C.c_int64]),
     'gpd_score_dev': (C.c_int, [C.c_void_p, c_void_pp, C.c_int32, C.c_void_p, C.c_int64, C.c_int, C.c_int, c_double_p,
                                 c_double_p, C.c_void_p, c_double_p, C.POINTER(C.c_int64), C.c_int64]),
+    'gpd_score_multi': (C.c_int, [C.c_void_p, c_void_pp, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int, c_int32_p,
+                                  C.c_int32, c_double_p, c_double_p, C.c_void_p, C.c_int32, c_double_p,
+                                  C.POINTER(C.c_int64), C.c_int64]),
     'gpd_dev_alloc': (C.c_int, [C.c_void_p, C.c_uint64, c_void_pp]),
     'gpd_dev_free': (C.c_int, [C.c_void_p, C.c_void_p]),
     'gpd_dev_upload': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),

@@ -357,7 +357,7 @@ static int plan_materialize(gpd_ctx* c, Plan& pl, Bump& bump) {
     GPD_CUDA(cudaMemcpyAsync(pl.views_dev, views.data(), sizeof(GpView) * views.size(), cudaMemcpyHostToDevice, c->stream));
     GPD_CUDA(cudaMemcpyAsync(pl.items_dev, items.data(), sizeof(Item) * items.size(), cudaMemcpyHostToDevice, c->stream));
     GPD_CUDA(cudaMemcpyAsync(pl.raws_dev, raws.data(), sizeof(RawOut) * M, cudaMemcpyHostToDevice, c->stream));
-    GPD_CUDA(cudaStreamSynchronize(c->stream));   // the host vectors go out of scope
+    // pageable-source cudaMemcpyAsync returns once the data is staged: the host vectors may go out of scope
     return 0;
 }
 
@@ -476,8 +476,8 @@ int gpd_create(int device, gpd_ctx** out) {
     GPD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     GPD_CUDA(cudaEventCreate(&c->t0));
     GPD_CUDA(cudaEventCreate(&c->t1));
-    GPD_CUDA(cudaMalloc(&c->best_val_dev, sizeof(double)));
-    GPD_CUDA(cudaMalloc(&c->best_idx_dev, sizeof(long long)));
+    GPD_CUDA(cudaMalloc(&c->best_val_dev, sizeof(double) * kMaxKinds));
+    GPD_CUDA(cudaMalloc(&c->best_idx_dev, sizeof(long long) * kMaxKinds));
     GPD_CUDA(cudaMalloc(&c->argmax_partial, argmax_partial_bytes()));
     *out = c;
     return 0;
@@ -1178,13 +1178,14 @@ int gpd_argmax(gpd_ctx* c, const double* dc, int64_t N, double* best_val, int64_
 // fused scoring
 // =================================================================================================
 static int score_impl(gpd_ctx* c, gpd_model* const* models, int32_t M, const double* X, bool x_on_device, int64_t N,
-                      int order, int kind, const double* noise, const double* pps, double* dc_out, bool dc_on_device,
-                      double* best_val, int64_t* best_idx, int64_t idx_offset) {
-    GPD_CHECK(c && models && X && noise && pps, "null argument");
+                      int order, const int32_t* kinds, int nk, const double* noise, const double* pps, double* dc_out,
+                      bool dc_on_device, double* best_val, int64_t* best_idx, int64_t idx_offset) {
+    GPD_CHECK(c && models && X && noise && pps && kinds, "null argument");
     GPD_CHECK(N >= 1, "no candidates");
     GPD_CHECK(M >= 1 && M <= 64, "number of models out of range (1..64)");
     GPD_CHECK(order == 1 || order == 2, "order must be 1 or 2");
-    GPD_CHECK(kind >= 0 && kind <= 4, "unknown criterion");
+    GPD_CHECK(nk >= 1 && nk <= kMaxKinds, "1..5 criteria per call");
+    for (int k = 0; k < nk; ++k) GPD_CHECK(kinds[k] >= 0 && kinds[k] <= 4, "unknown criterion");
     GPD_CUDA(cudaSetDevice(c->device));
     const int E = models[0]->E, D = models[0]->D;
     int maxP = 0;
@@ -1194,7 +1195,7 @@ static int score_impl(gpd_ctx* c, gpd_model* const* models, int32_t M, const dou
         maxP = std::max(maxP, models[m]->P);
     }
     Plan pl;
-    size_t extra = sizeof(double) * ((size_t)M * E + (size_t)M * E * E + 1) + sizeof(double) * criterion_work_doubles(1, M, E);
+    size_t extra = sizeof(double) * ((size_t)M * E + (size_t)M * E * E + nk) + sizeof(double) * criterion_work_doubles(1, M, E);
     if (!x_on_device) extra += sizeof(double) * D;
     if (order == 2) extra += sizeof(double) * ((size_t)E * maxP * maxP + E);
     GPD_TRY(plan_build(c, models, M, order_flags(order), N, extra, 0, pl));
@@ -1206,7 +1207,7 @@ static int score_impl(gpd_ctx* c, gpd_model* const* models, int32_t M, const dou
     double* X_stage = x_on_device ? nullptr : bump.take<double>((size_t)Nc * D);
     double* mu_all = bump.take<double>((size_t)Nc * M * E);
     double* S_all = bump.take<double>((size_t)Nc * M * E * E);
-    double* dc_dev = bump.take<double>((size_t)Nc);
+    double* dc_dev = bump.take<double>((size_t)Nc * nk);
     double* work = bump.take<double>(criterion_work_doubles(Nc, M, E));
     double* tmpA = order == 2 ? bump.take<double>((size_t)Nc * E * maxP * maxP) : nullptr;
     double* tmp_s2 = order == 2 ? bump.take<double>((size_t)Nc * E) : nullptr;
@@ -1238,38 +1239,51 @@ static int score_impl(gpd_ctx* c, gpd_model* const* models, int32_t M, const dou
             GPD_TRY(launch_assemble(s, order, nc, E, mo->P, b.mu, b.ldmu, b.s2, b.dmu, b.d2mu, b.d2s2, Sigma_dev,
                                     S_all + (size_t)m * E * E, M * E * E, tmpA, tmp_s2));
         }
-        double* dc_target = (dc_out && dc_on_device) ? dc_out + start : dc_dev;
-        {
-            Span sp(c, F_CRIT, 2, 0);
-            GPD_TRY(launch_criterion(s, kind, mu_all, S_all, nc, M, E, d_noise, d_pps, dc_target, work));
+        for (int k = 0; k < nk; ++k) {
+            double* dc_target = (dc_out && dc_on_device) ? dc_out + (size_t)k * N + start : dc_dev + (size_t)k * Nc;
+            {
+                Span sp(c, F_CRIT, 2, 0);
+                GPD_TRY(launch_criterion(s, kinds[k], mu_all, S_all, nc, M, E, d_noise, d_pps, dc_target, work));
+            }
+            {
+                Span sp(c, F_ARGMAX, 2, 0);
+                GPD_TRY(launch_argmax(s, dc_target, nc, idx_offset + start, c->best_val_dev + k, c->best_idx_dev + k,
+                                      start == 0, c->argmax_partial));
+            }
+            if (dc_out && !dc_on_device)
+                GPD_CUDA(cudaMemcpyAsync(dc_out + (size_t)k * N + start, dc_target, sizeof(double) * nc,
+                                         cudaMemcpyDeviceToHost, s));
         }
-        {
-            Span sp(c, F_ARGMAX, 2, 0);
-            GPD_TRY(launch_argmax(s, dc_target, nc, idx_offset + start, c->best_val_dev, c->best_idx_dev, start == 0,
-                                  c->argmax_partial));
-        }
-        if (dc_out && !dc_on_device)
-            GPD_CUDA(cudaMemcpyAsync(dc_out + start, dc_dev, sizeof(double) * nc, cudaMemcpyDeviceToHost, s));
     }
-    long long bi = -1;
-    double bv = 0;
-    GPD_CUDA(cudaMemcpyAsync(&bv, c->best_val_dev, sizeof(double), cudaMemcpyDeviceToHost, s));
-    GPD_CUDA(cudaMemcpyAsync(&bi, c->best_idx_dev, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    long long bi[kMaxKinds];
+    double bv[kMaxKinds];
+    GPD_CUDA(cudaMemcpyAsync(bv, c->best_val_dev, sizeof(double) * nk, cudaMemcpyDeviceToHost, s));
+    GPD_CUDA(cudaMemcpyAsync(bi, c->best_idx_dev, sizeof(long long) * nk, cudaMemcpyDeviceToHost, s));
     GPD_CUDA(cudaStreamSynchronize(s));
-    if (best_val) *best_val = bv;
-    if (best_idx) *best_idx = bi;
+    for (int k = 0; k < nk; ++k) {
+        if (best_val) best_val[k] = bv[k];
+        if (best_idx) best_idx[k] = bi[k];
+    }
     return 0;
 }
 
 int gpd_score(gpd_ctx* c, gpd_model* const* models, int32_t M, const double* X, int64_t N, int order, int kind,
               const double* noise, const double* pps, double* dc_out, double* best_val, int64_t* best_idx,
               int64_t idx_offset) {
-    return score_impl(c, models, M, X, false, N, order, kind, noise, pps, dc_out, false, best_val, best_idx, idx_offset);
+    const int32_t k = kind;
+    return score_impl(c, models, M, X, false, N, order, &k, 1, noise, pps, dc_out, false, best_val, best_idx, idx_offset);
 }
 int gpd_score_dev(gpd_ctx* c, gpd_model* const* models, int32_t M, const double* X_dev, int64_t N, int order, int kind,
                   const double* noise, const double* pps, double* dc_out_dev, double* best_val, int64_t* best_idx,
                   int64_t idx_offset) {
-    return score_impl(c, models, M, X_dev, true, N, order, kind, noise, pps, dc_out_dev, true, best_val, best_idx, idx_offset);
+    const int32_t k = kind;
+    return score_impl(c, models, M, X_dev, true, N, order, &k, 1, noise, pps, dc_out_dev, true, best_val, best_idx, idx_offset);
+}
+int gpd_score_multi(gpd_ctx* c, gpd_model* const* models, int32_t M, const double* X, int32_t x_on_device, int64_t N,
+                    int order, const int32_t* kinds, int32_t nkinds, const double* noise, const double* pps,
+                    double* dc_out, int32_t dc_on_device, double* best_val, int64_t* best_idx, int64_t idx_offset) {
+    return score_impl(c, models, M, X, x_on_device != 0, N, order, kinds, nkinds, noise, pps, dc_out, dc_on_device != 0,
+                      best_val, best_idx, idx_offset);
 }
 
 // ---- layout self-description --------------------------------------------------------------------

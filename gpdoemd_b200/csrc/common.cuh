@@ -14,6 +14,7 @@ constexpr int kMaxXDims = 8;     // active (non-binary) design dimensions handle
 constexpr int kMaxP = 16;        // model parameters
 constexpr int kMaxE = 8;         // outputs (register-resident E x E criteria)
 constexpr int kMaxBinary = 6;
+constexpr int kMaxKinds = 5;      // criteria scored in one fused pass
 
 // Device-side view of one GP (array in global memory, indexed by work items).
 struct GpView {

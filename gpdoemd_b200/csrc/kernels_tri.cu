@@ -89,44 +89,134 @@ struct TriArgs {
     int chunk_n;
 };
 
-template <int WM, int WN, bool DIAG>
+// One k4 step for the 8-row blocks [LO, HI) of this warp's row group.
+template <int MB, int NB, int LO, int HI>
+__device__ __forceinline__ void kstep(double (&acc)[MB][NB][2], const double (&a)[MB], const double (&b)[NB]) {
+#pragma unroll
+    for (int mb = LO; mb < HI; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+}
+// Diagonal tiles: the zero 8 x 4 sub-blocks of the triangular factor are skipped with REAL (warp-uniform)
+// branches.  A predicated-off DMMA still occupies the FP64 tensor pipe for its full issue interval
+// (measured: profiles/r01_tri_c2_ncu.md), so predication alone saves nothing.
+//   forward  (lower): blocks mb >= v are non-zero  -> run [v, MB)
+//   backward (upper): blocks mb <  v are non-zero  -> run [0, v)
+template <int MB, int NB, bool BWD, int C>
+__device__ __forceinline__ void kstep_bounded(int v, double (&acc)[MB][NB][2], const double (&a)[MB],
+                                              const double (&b)[NB]) {
+    if (v == C) {
+        if (BWD) kstep<MB, NB, 0, C>(acc, a, b);
+        else kstep<MB, NB, C, MB>(acc, a, b);
+    } else if constexpr (C < MB) {
+        kstep_bounded<MB, NB, BWD, C + 1>(v, acc, a, b);
+    }
+}
+
+template <int WM, int WN, bool DIAG, bool BWD>
 __device__ __forceinline__ void compute_chunk(const double* __restrict__ sA, const double* __restrict__ sB, int lane,
-                                              int wm, int wn, int chunk_in_blk, int backward,
+                                              int wm, int wn, int chunk_in_blk,
                                               double (&acc)[16 / WM][16 / WN][2]) {
     constexpr int MB = 16 / WM, NB = 16 / WN;
     const int lq = lane & 3, lr = lane >> 2;
+    if (DIAG) {
+        // whole chunk zero for this warp's rows?  rows [wm*MB*8, (wm+1)*MB*8), k in [16c, 16c+16)
+        const int rlo = wm * MB * 8, rhi = rlo + MB * 8 - 1, klo = chunk_in_blk * kChunkK, khi = klo + kChunkK - 1;
+        if (BWD ? (khi < rlo) : (klo > rhi)) return;
+    }
+    const double* __restrict__ pa = sA + ((wm * MB * 2) * 32 + lane) * 2;
+    // b_index(k, t), k = ks*4 + lq, t = (wn*NB + nb)*8 + lr: the swizzle (k & 3) << 2 == lq << 2 flips bits 2..3 of t,
+    // i.e. it depends on lr and on the parity of nb only -> two lane-constant bases, even and odd nb
+    static_assert(NB % 2 == 0, "NB must be even");
+    const double* __restrict__ pb0 = sB + lq * kBlk + ((wn * NB * 8 + lr) ^ (lq << 2));
+    const double* __restrict__ pb1 = sB + lq * kBlk + ((wn * NB * 8 + 8 + lr) ^ (lq << 2));
 #pragma unroll
     for (int kp = 0; kp < 2; ++kp) {
         double2 a2[MB];
 #pragma unroll
-        for (int mb = 0; mb < MB; ++mb)
-            a2[mb] = *reinterpret_cast<const double2*>(sA + a_index(wm * MB + mb, kp * 2, lane));
+        for (int mb = 0; mb < MB; ++mb) a2[mb] = *reinterpret_cast<const double2*>(pa + (mb * 2 + kp) * 64);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int ks = kp * 2 + h;
-            double b[NB];
-            const int krow = ks * 4 + lq;
+            double a[MB], b[NB];
 #pragma unroll
-            for (int nb = 0; nb < NB; ++nb) b[nb] = sB[b_index(krow, (wn * NB + nb) * 8 + lr)];
-            const int k0 = chunk_in_blk * kChunkK + ks * 4;     // first k of this k4 step inside the 128 block
+            for (int mb = 0; mb < MB; ++mb) a[mb] = h ? a2[mb].y : a2[mb].x;
 #pragma unroll
-            for (int mb = 0; mb < MB; ++mb) {
-                if (DIAG) {
-                    const int r = (wm * MB + mb) * 8;           // first row of this 8-row block
-                    // forward (lower): entries with k <= row ; backward (upper): entries with k >= row
-                    const bool zero = backward ? (k0 + 3 < r) : (k0 > r + 7);
-                    if (zero) continue;
-                }
-                const double a = h ? a2[mb].y : a2[mb].x;
-#pragma unroll
-                for (int nb = 0; nb < NB; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a, b[nb]);
+            for (int nb = 0; nb < NB; ++nb) b[nb] = ((nb & 1) ? pb1 : pb0)[ks * 4 * kBlk + (nb >> 1) * 16];
+            if (DIAG) {
+                const int k0 = chunk_in_blk * kChunkK + ks * 4;
+                int v = (k0 >> 3) - wm * MB + (BWD ? 1 : 0);
+                v = v < 0 ? 0 : (v > MB ? MB : v);
+                kstep_bounded<MB, NB, BWD, 0>(v, acc, a, b);
+            } else {
+                kstep<MB, NB, 0, MB>(acc, a, b);
             }
         }
     }
 }
 
-template <int WM, int WN>
-__global__ void __launch_bounds__((WM * WN + 1) * 32, 1) tri_kernel(const TriArgs args) {
+// Chunk-stream generator run by ONE thread per CTA (lane 0 of warp 0): walks the flat sequence of
+// (work item, row block I, k block q, chunk c) and issues the two 16 KiB bulk copies of each chunk.
+// The packed factor stores the chunks of one item in exactly this order, so the A address is sequential.
+struct ChunkStream {
+    int w, j, total, I, q, c, len, nblk;
+    const double* A;
+    const double* B;
+    int stage;
+    uint32_t phase;
+};
+
+template <bool BWD>
+__device__ __forceinline__ void stream_seek_item(ChunkStream& ps, const TriArgs& args, int nwork) {
+    // position on the next work item of this CTA that has candidates; ps.w >= nwork means exhausted
+    for (; ps.w < nwork; ps.w += gridDim.x) {
+        const Item it = args.items[ps.w / args.nwork_rhs];
+        const int a = ps.w % args.nwork_rhs;
+        const GpView& g = args.gps[it.gp];
+        const int count = g.count ? *g.count : args.chunk_n;
+        if (it.tile * kBlk >= count) continue;
+        ps.nblk = g.nblk;
+        ps.A = BWD ? g.LinvB : g.LinvF;
+        ps.B = args.panels_in + g.panel_off * args.in_stride + ((size_t)(it.tile * args.in_stride + a) * g.n_pad) * kBlk;
+        ps.total = (int)packed_tiles(g.nblk) * kChunksPerBlk;
+        ps.j = 0;
+        ps.I = 0;
+        ps.q = 0;
+        ps.c = 0;
+        ps.len = tile_run_len(g.nblk, 0, BWD);
+        return;
+    }
+}
+
+template <bool BWD>
+__device__ __forceinline__ void stream_issue(ChunkStream& ps, const TriArgs& args, int nwork, TriSmem& sm) {
+    if (ps.w >= nwork) return;
+    mbar_wait(smem_u32(&sm.empty[ps.stage]), ps.phase ^ 1);
+    const uint32_t fb = smem_u32(&sm.full[ps.stage]);
+    mbar_expect_tx(fb, 2 * kChunkBytes);
+    const int kb = tile_run_kfirst(ps.I, BWD) + ps.q;
+    bulk_g2s(smem_u32(sm.A[ps.stage]), ps.A + (size_t)ps.j * kChunkElems, kChunkBytes, fb);
+    bulk_g2s(smem_u32(sm.B[ps.stage]), ps.B + ((size_t)kb * kBlk + ps.c * kChunkK) * kBlk, kChunkBytes, fb);
+    if (++ps.stage == kStages) { ps.stage = 0; ps.phase ^= 1; }
+    ++ps.j;
+    if (++ps.c == kChunksPerBlk) {
+        ps.c = 0;
+        if (++ps.q == ps.len) {
+            ps.q = 0;
+            ++ps.I;
+            ps.len = tile_run_len(ps.nblk, ps.I, BWD);
+        }
+    }
+    if (ps.j == ps.total) {
+        ps.w += gridDim.x;
+        stream_seek_item<BWD>(ps, args, nwork);
+    }
+}
+
+// 16 (WM=4) or 8 (WM=2) warps, all of them DMMA consumers; no dedicated producer warp: the register file is
+// allocated in groups of 4 warps, so a 17th warp would cost every thread a quarter of its registers.
+template <int WM, int WN, bool BWD>
+__global__ void __launch_bounds__(WM * WN * 32, 1) tri_kernel(const TriArgs args) {
     constexpr int NCW = WM * WN;            // consumer warps
     constexpr int MB = 16 / WM, NB = 16 / WN;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -147,39 +237,17 @@ __global__ void __launch_bounds__((WM * WN + 1) * 32, 1) tri_kernel(const TriArg
     int stage = 0;
     uint32_t phase = 0;
 
-    if (warp == NCW) {
-        // ===== producer: one lane streams A (packed factor) and B (RHS panel) chunks =====
-        if (lane != 0) return;
-        for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
-            const Item it = args.items[w / args.nwork_rhs];
-            const int a = w % args.nwork_rhs;
-            const GpView& g = args.gps[it.gp];
-            const int count = g.count ? *g.count : args.chunk_n;
-            if (it.tile * kBlk >= count) continue;
-            const int nblk = g.nblk, n_pad = g.n_pad;
-            const double* pack = args.backward ? g.LinvB : g.LinvF;
-            const double* Bsrc = args.panels_in + g.panel_off * args.in_stride +
-                                 ((size_t)(it.tile * args.in_stride + a) * n_pad) * kBlk;
-            for (int I = 0; I < nblk; ++I) {
-                const double* Arun = pack + tile_run_base(nblk, I, args.backward) * (long long)kTileElems;
-                const int len = tile_run_len(nblk, I, args.backward);
-                const int kfirst = tile_run_kfirst(I, args.backward);
-                for (int q = 0; q < len; ++q) {
-                    const double* At = Arun + (size_t)q * kTileElems;
-                    const double* Bt = Bsrc + (size_t)(kfirst + q) * kBlk * kBlk;
-                    for (int c = 0; c < kChunksPerBlk; ++c) {
-                        mbar_wait(smem_u32(&sm.empty[stage]), phase ^ 1);
-                        const uint32_t fb = smem_u32(&sm.full[stage]);
-                        mbar_expect_tx(fb, 2 * kChunkBytes);
-                        bulk_g2s(smem_u32(sm.A[stage]), At + (size_t)c * kChunkElems, kChunkBytes, fb);
-                        bulk_g2s(smem_u32(sm.B[stage]), Bt + (size_t)c * kChunkElems, kChunkBytes, fb);
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
-                    }
-                }
-            }
-        }
-        return;
+    const bool is_producer = (threadIdx.x == 0);
+    ChunkStream ps;
+    ps.w = blockIdx.x;
+    ps.stage = 0;
+    ps.phase = 0;
+    if (is_producer) {
+        stream_seek_item<BWD>(ps, args, nwork);
+#pragma unroll 1
+        for (int k = 0; k < kStages - 1; ++k) stream_issue<BWD>(ps, args, nwork, sm);
     }
+    __syncwarp();
 
     // ===== consumers: DMMA over the chunk stream =====
     const int wm = warp / WN, wn = warp % WN;       // warp w lives on SMSP w%4: every SMSP sees all row groups
@@ -199,25 +267,30 @@ __global__ void __launch_bounds__((WM * WN + 1) * 32, 1) tri_kernel(const TriArg
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) csq[nb][0] = csq[nb][1] = 0.0;
 
+#pragma unroll 1
         for (int I = 0; I < nblk; ++I) {
             double acc[MB][NB][2];
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
-            const int len = tile_run_len(nblk, I, args.backward);
-            const int qdiag = args.backward ? 0 : len - 1;
+            const int len = tile_run_len(nblk, I, BWD);
+            const int qdiag = BWD ? 0 : len - 1;
+#pragma unroll 1
             for (int q = 0; q < len; ++q) {
                 const bool diag = (q == qdiag);
+#pragma unroll 1
                 for (int c = 0; c < kChunksPerBlk; ++c) {
                     mbar_wait(smem_u32(&sm.full[stage]), phase);
                     if (diag)
-                        compute_chunk<WM, WN, true>(sm.A[stage], sm.B[stage], lane, wm, wn, c, args.backward, acc);
+                        compute_chunk<WM, WN, true, BWD>(sm.A[stage], sm.B[stage], lane, wm, wn, c, acc);
                     else
-                        compute_chunk<WM, WN, false>(sm.A[stage], sm.B[stage], lane, wm, wn, c, args.backward, acc);
+                        compute_chunk<WM, WN, false, BWD>(sm.A[stage], sm.B[stage], lane, wm, wn, c, acc);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stage]));
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (is_producer) stream_issue<BWD>(ps, args, nwork, sm);
+                    __syncwarp();
                 }
             }
             // ---- epilogue of row block I: optional store of V, running column sums of squares ----
@@ -249,7 +322,7 @@ __global__ void __launch_bounds__((WM * WN + 1) * 32, 1) tri_kernel(const TriArg
                     s += __shfl_xor_sync(0xffffffffu, s, 16);
                     if (lr == 0) sm.colsum[wm][(wn * NB + nb) * 8 + 2 * lq + j] = s;
                 }
-            consumer_bar(NCW * 32);
+            __syncthreads();
             if (threadIdx.x < kBlk) {
                 const int t = threadIdx.x;
                 double tot = 0.0;
@@ -262,7 +335,7 @@ __global__ void __launch_bounds__((WM * WN + 1) * 32, 1) tri_kernel(const TriArg
                     raw.gram[((size_t)g.out_e * args.chunk_n + cand) * args.ng] = tot;
                 }
             }
-            consumer_bar(NCW * 32);
+            __syncthreads();
         }
     }
 }
@@ -270,8 +343,10 @@ __global__ void __launch_bounds__((WM * WN + 1) * 32, 1) tri_kernel(const TriArg
 static bool g_tri_attr_done = false;
 int tri_setup_attributes() {
     if (g_tri_attr_done) return 0;
-    GPD_CUDA(cudaFuncSetAttribute(tri_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TriSmem)));
-    GPD_CUDA(cudaFuncSetAttribute(tri_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TriSmem)));
+    GPD_CUDA(cudaFuncSetAttribute(tri_kernel<4, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TriSmem)));
+    GPD_CUDA(cudaFuncSetAttribute(tri_kernel<4, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TriSmem)));
+    GPD_CUDA(cudaFuncSetAttribute(tri_kernel<2, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TriSmem)));
+    GPD_CUDA(cudaFuncSetAttribute(tri_kernel<2, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TriSmem)));
     g_tri_attr_done = true;
     return 0;
 }
@@ -296,10 +371,13 @@ int launch_tri(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int
     args.chunk_n = chunk_n;
     long long nwork = (long long)nitems * nwork_rhs;
     int grid = (int)(nwork < num_sms ? nwork : num_sms);
-    if (variant == 1)
-        tri_kernel<2, 4><<<grid, (2 * 4 + 1) * 32, sizeof(TriSmem), s>>>(args);
-    else
-        tri_kernel<4, 4><<<grid, (4 * 4 + 1) * 32, sizeof(TriSmem), s>>>(args);
+    if (variant == 1) {
+        if (backward) tri_kernel<2, 4, true><<<grid, 2 * 4 * 32, sizeof(TriSmem), s>>>(args);
+        else tri_kernel<2, 4, false><<<grid, 2 * 4 * 32, sizeof(TriSmem), s>>>(args);
+    } else {
+        if (backward) tri_kernel<4, 4, true><<<grid, 4 * 4 * 32, sizeof(TriSmem), s>>>(args);
+        else tri_kernel<4, 4, false><<<grid, 4 * 4 * 32, sizeof(TriSmem), s>>>(args);
+    }
     GPD_CUDA(cudaGetLastError());
     return 0;
 }

@@ -27,6 +27,36 @@ def _prep(models, criterion, noise_var, pps):
     return _lib.CRITERION_IDS[criterion], _lib.as_f64(noise), _lib.as_f64(pps_n), handles
 
 
+def score_designs_multi(models, X, criteria, order=1, noise_var=None, pps=None, return_dc=True, idx_offset=0,
+                        x_dev=None, N=None, dc_dev=None):
+    """Several criteria in one pass over the candidates -> {name: (best_index, best_value, dc or None)}.
+
+    X is a host (N, dim_x) array, or pass ``x_dev`` (device pointer) and ``N`` for resident candidates
+    (then ``dc_dev`` may be a device pointer to [len(criteria)][N] doubles).
+    """
+    dev = models[0]._device
+    ctx = get_context(dev)
+    _, noise, pps_n, handles = _prep(models, criteria[0], noise_var, pps)
+    kinds = np.array([_lib.CRITERION_IDS[c] for c in criteria], dtype=np.int32)
+    nk = len(kinds)
+    bv = np.zeros(nk)
+    bi = (C.c_int64 * nk)()
+    if x_dev is None:
+        X = _lib.as_f64(X)
+        N = len(X)
+        dc = np.empty((nk, N)) if return_dc else None
+        xp, x_on_dev = X.ctypes.data_as(C.c_void_p), 0
+        dcp, dc_on_dev = (dc.ctypes.data_as(C.c_void_p) if return_dc else None), 0
+    else:
+        dc = None
+        xp, x_on_dev = x_dev, 1
+        dcp, dc_on_dev = dc_dev, 1
+    check(ctx.lib.gpd_score_multi(ctx.handle, C.cast(handles, _lib.c_void_pp), len(models), xp, x_on_dev, int(N), order,
+                                  kinds.ctypes.data_as(_lib.c_int32_p), nk, dptr(noise), dptr(pps_n), dcp, dc_on_dev,
+                                  dptr(bv), bi, int(idx_offset)))
+    return {c: (int(bi[k]), float(bv[k]), None if dc is None else dc[k]) for k, c in enumerate(criteria)}
+
+
 def score_designs(models, X, order=1, criterion='BH', noise_var=None, pps=None, return_dc=True, idx_offset=0):
     """-> (best_index, best_value, dc or None).  X: (N, dim_x) host array in original units."""
     X = _lib.as_f64(X)

@@ -13,7 +13,7 @@ CONFIGS = {
 }
 
 
-def model_data(seed, E, D, P, n, n_binary=0):
+def model_data(seed, E, D, P, n, n_binary=0, gp_noise=1e-6, kernel=None):
     """Training set and hyper-parameters of one model.
 
     Z (n, D+P) original units, Y (n, E) smooth deterministic responses (a surrogate is trained on
@@ -33,8 +33,10 @@ def model_data(seed, E, D, P, n, n_binary=0):
         Y[:, e] = (1.0 + e) * np.sin(3.0 * U.dot(w) / np.sqrt(D + P) + 0.7 * e) + 0.3 * U.dot(rng.normal(size=D + P))
     R = 2 ** n_binary
     Dx = D - n_binary
-    hyp = [[np.r_[rng.uniform(0.5, 2.0), rng.uniform(0.3, 2.0, Dx), rng.uniform(0.5, 2.0), rng.uniform(0.3, 2.0, P), 1e-6]
-            for _ in range(R)] for _ in range(E)]
+    # GPy flat order: kernx.variance, kernx.lengthscale[, kernx.power], kernp.variance, kernp.lengthscale[, kernp.power], noise
+    pw = (lambda: [rng.uniform(1.0, 3.0)]) if kernel == 'RatQuad' else (lambda: [])
+    hyp = [[np.r_[rng.uniform(0.5, 2.0), rng.uniform(0.3, 2.0, Dx), pw(), rng.uniform(0.5, 2.0), rng.uniform(0.3, 2.0, P), pw(),
+                  gp_noise] for _ in range(R)] for _ in range(E)]
     pmean = plo + rng.uniform(0.25, 0.75, P) * (phi - plo)
     A = rng.normal(size=(P, P))
     Sigma = A.dot(A.T) / P * 1e-2 * np.outer(phi - plo, phi - plo)
@@ -49,11 +51,11 @@ def candidates(seed, N, D, xlo, xhi, n_binary=0):
     return X
 
 
-def build_models(cls, seed, M, E, D, P, n, kernel, n_binary=0, kernel_lookup=None, **kw):
+def build_models(cls, seed, M, E, D, P, n, kernel, n_binary=0, kernel_lookup=None, gp_noise=1e-6, **kw):
     """Instantiate ``cls`` (gpdoemd_b200.GPModel or an API-compatible class) for M rival models."""
     models, datas = [], []
     for m in range(M):
-        d = model_data(seed * 1000 + m, E, D, P, n, n_binary)
+        d = model_data(seed * 1000 + m, E, D, P, n, n_binary, gp_noise, kernel)
         mo = cls({'name': 'm%d' % m, 'call': (lambda x, p: None), 'dim_x': D, 'dim_p': P, 'num_outputs': E,
                   'meas_noise_var': 0.01, 'binary_variables': d['binary']}, **kw)
         k = kernel if kernel_lookup is None else kernel_lookup[kernel]

@@ -168,6 +168,13 @@ int  gpd_score(gpd_ctx* ctx, gpd_model* const* models, int32_t M, const double* 
 int  gpd_score_dev(gpd_ctx* ctx, gpd_model* const* models, int32_t M, const double* X_dev, int64_t N,
                    int order, int kind, const double* noise, const double* pps,
                    double* dc_out_dev, double* best_val, int64_t* best_idx, int64_t idx_offset);
+/* several criteria in ONE pass over the candidates (the demo scores all five on the same mu, S:
+ * demos/case_study.py:289-293).  X / dc_out are host or device pointers according to the two flags;
+ * dc_out (may be NULL) is [nkinds][N]; best_val / best_idx have nkinds entries. */
+int  gpd_score_multi(gpd_ctx* ctx, gpd_model* const* models, int32_t M, const double* X, int32_t x_on_device,
+                     int64_t N, int order, const int32_t* kinds, int32_t nkinds, const double* noise,
+                     const double* pps, double* dc_out, int32_t dc_on_device, double* best_val,
+                     int64_t* best_idx, int64_t idx_offset);
 /* device buffer helpers so a host language without a CUDA binding can stage candidates once */
 int  gpd_dev_alloc(gpd_ctx* ctx, uint64_t bytes, void** out_dev);
 int  gpd_dev_free(gpd_ctx* ctx, void* dev);

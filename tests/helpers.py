@@ -7,9 +7,9 @@ from oracle import gpy_kernels
 from oracle.model import OracleGPModel
 
 
-def oracle_models(seed, M, E, D, P, n, kernel, n_binary=0):
+def oracle_models(seed, M, E, D, P, n, kernel, n_binary=0, gp_noise=1e-6):
     return synthetic.build_models(OracleGPModel, seed, M, E, D, P, n, kernel, n_binary,
-                                  kernel_lookup=gpy_kernels.KERNELS)
+                                  kernel_lookup=gpy_kernels.KERNELS, gp_noise=gp_noise)
 
 
 def gpu_models(oracle_ms):
