@@ -1,0 +1,141 @@
+"""Host-side logic of gpdoemd_b200.GPModel without a GPU: the reference's property validation, training-data
+normalisation, assertion order and save/load (tests/test_models/test_surrogate_model.py:63-216,
+tests/test_models/test_gp_model.py:61-137 of the reference), and the host exact-GP setup vs the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+import gpdoemd_b200 as g
+from gpdoemd_b200 import synthetic
+from gpdoemd_b200.gp_state import GPState
+
+
+def _dict(**kw):
+    d = {'name': 'm', 'call': lambda x, p: x, 'dim_x': 3, 'dim_p': 2, 'num_outputs': 2}
+    d.update(kw)
+    return d
+
+
+def test_constructor_validation():
+    m = g.GPModel(_dict())
+    assert m.dim_b == 0 and m.non_binary_variables == [0, 1, 2]
+    assert m.gp_noise_var == 1e-6 and np.array_equal(m.meas_noise_var, [1., 1.])
+    with pytest.raises(AssertionError):
+        g.GPModel(_dict(dim_x=0))
+    with pytest.raises(AssertionError):
+        g.GPModel(_dict(num_outputs=1.5))
+    with pytest.raises(AssertionError):
+        g.GPModel(_dict(name=3))
+    with pytest.raises(AssertionError):
+        g.GPModel(_dict(binary_variables=[3]))
+    with pytest.raises(AssertionError):
+        g.GPModel(_dict(binary_variables=[0.5]))
+    with pytest.raises(ValueError):
+        g.GPModel(_dict(binary_variables='a'))
+    assert g.GPModel(_dict(binary_variables=1)).binary_variables == [1]
+    with pytest.raises(AssertionError):
+        g.GPModel(_dict(gp_noise_var=-1.0))
+    with pytest.raises(AssertionError):
+        g.GPModel(_dict(meas_noise_var=np.array([1., -1.])))
+
+
+def test_pmean_sigma_properties():
+    m = g.GPModel(_dict())
+    assert m.pmean is None and m.Sigma is None
+    with pytest.raises(AssertionError):
+        m.pmean = [1, 2]
+    with pytest.raises(AssertionError):
+        m.pmean = np.zeros(3)
+    m.pmean = np.array([1., 2.])
+    with pytest.raises(AssertionError):
+        m.Sigma = np.eye(3)
+    S = np.eye(2)
+    m.Sigma = S
+    S[0, 0] = 5
+    assert m.Sigma[0, 0] == 1           # the setter copies (model.py:153)
+    del m.pmean
+    assert m.pmean is None and np.array_equal(m._old_pmean, [1., 2.])
+
+
+def test_training_data_normalisation():
+    rng = np.random.default_rng(0)
+    m = g.GPModel(_dict(binary_variables=[2]))
+    Z = np.c_[rng.uniform(2, 5, (20, 2)), rng.integers(0, 2, 20), rng.uniform(-1, 1, (20, 2))]
+    Y = rng.normal(3, 2, (20, 2))
+    with pytest.raises(AssertionError):
+        m.set_training_data(Z[:, :4], Y)
+    m.set_training_data(Z, Y)
+    assert m.Z.shape == (20, 5) and m.Z.min() >= 0 and m.Z.max() <= 1
+    assert m.zmin[2] == 0 and m.zmax[2] == 1                 # binary columns keep 0/1 (surrogate_model.py:80-82)
+    assert np.allclose(m.Y.mean(0), 0) and np.allclose(m.Y.std(0), 1)
+    assert np.allclose(m.trans_z(m.Z, back=True), Z) and np.allclose(m.trans_y(m.Y, back=True), Y)
+    assert m.X.shape == (20, 3) and m.P.shape == (20, 2) and len(m.xmin) == 3 and len(m.pmax) == 2
+    m.pmean = np.array([0.1, -0.2])
+    ZZ = m.get_Z(m.X[:4])
+    assert ZZ.shape == (4, 5) and np.allclose(ZZ[:, 3:], m.trans_p(m.pmean))
+    with pytest.raises(AssertionError):
+        m.get_Z(m.X[:4], np.zeros((3, 2)))
+    # the three-argument form (surrogate_model.py:159-165)
+    m.set_training_data(Z[:, :3], Z[:, 3:], Y)
+    assert m.Z.shape == (20, 5)
+
+
+def test_predict_assertion_order():
+    m = g.GPModel(_dict())
+    X = np.zeros((2, 3))
+    with pytest.raises(AssertionError):
+        m.predict(X)                      # pmean missing
+    m.pmean = np.zeros(2)
+    with pytest.raises(AssertionError):
+        m.predict(X)                      # Z / Y missing
+    rng = np.random.default_rng(1)
+    m.set_training_data(rng.uniform(size=(10, 5)), rng.normal(size=(10, 2)))
+    with pytest.raises(AssertionError):
+        m.predict(X)                      # hyp missing
+    with pytest.raises(NotImplementedError):
+        m.gp_optimise()
+
+
+def test_gp_surrogate_layout_and_hyp_roundtrip(tmp_path):
+    ms, ds = synthetic.build_models(g.GPModel, 4, M=1, E=2, D=3, P=2, n=40, kernel='Matern52', n_binary=1)
+    m = ms[0]
+    assert len(m.gps) == 2 and len(m.gps[0]) == 2           # E lists of 2^b GPs
+    for e in range(2):
+        for r in range(2):
+            assert np.array_equal(m.gps[e][r][:], m.hyp[e][r])
+    assert m.kern_p is m.kern_x                              # gp_model.py:60 quirk
+    f = str(tmp_path / 'model')
+    m.save(f)
+    m2 = g.GPModel(_dict(dim_p=2, binary_variables=[2]))
+    m2.load(f)
+    assert np.allclose(m2.Z, m.Z, atol=1e-10) and np.allclose(m2.Y, m.Y, atol=1e-10)
+    assert np.array_equal(m2.pmean, m.pmean) and np.array_equal(m2.Sigma, m.Sigma)
+    m.clear_model()
+    assert m.Z is None and m.Y is None and m.hyp is None and m.pmean is None and m.Sigma is None
+
+
+@pytest.mark.parametrize('kernel', ['RBF', 'Exponential', 'Matern32', 'Matern52', 'RatQuad'])
+def test_host_exact_gp_matches_oracle_state(kernel):
+    """The host setup (ExactGP: K, Cholesky, alpha) reproduces the oracle's GPy restatement bit for bit,
+    and GPState.from_gp reads the same arrays from either object."""
+    oms, ds = helpers.oracle_models(6, M=1, E=1, D=3, P=2, n=50, kernel=kernel)
+    gms, _ = synthetic.build_models(g.GPModel, 6, M=1, E=1, D=3, P=2, n=50, kernel=kernel)
+    go, gg = oms[0].gps[0][0], gms[0].gps[0][0]
+    assert np.array_equal(go.posterior.woodbury_chol, gg.posterior.woodbury_chol)
+    assert np.array_equal(go.posterior.woodbury_vector, gg.posterior.woodbury_vector)
+    so, sg = GPState.from_gp(go, 3, 2), GPState.from_gp(gg, 3, 2)
+    for k in ('Z', 'alpha', 'L', 'ls_x', 'ls_p', 'x_active'):
+        assert np.array_equal(getattr(so, k), getattr(sg, k)), k
+    assert (so.kernel, so.var_x, so.var_p, so.power_x) == (sg.kernel, sg.var_x, sg.var_p, sg.power_x) and so.kernel == kernel
+
+
+def test_from_reference_adopts_everything():
+    oms, ds = helpers.oracle_models(8, M=1, E=2, D=3, P=2, n=30, kernel='RBF', n_binary=1)
+    om = oms[0]
+    m = g.GPModel.from_reference(om)
+    assert m.binary_variables == om.binary_variables and m.dim_b == 1
+    for k in ('xmin', 'xmax', 'pmin', 'pmax', 'ymean', 'ystd', 'pmean', 'Sigma'):
+        assert np.array_equal(getattr(m, k), getattr(om, k)), k
+    assert m.gps is om.gps and m.hyp is om.hyp
