@@ -1,0 +1,283 @@
+// K1: fused x-kernel row + mean/derivative contraction + right-hand-side panels.
+//
+// Reference arithmetic: GPy Stationary.K for kx(x*, X) (gp_model.py:199,232,266) followed by the products
+// with alpha / the p-part that GPy's predictive_gradients / gradients_XX form (gp_model.py:217,233,275);
+// one transcendental per (candidate, training point).
+//
+// Work item = (GP, tile of 128 candidates).  A CTA of 128 threads is split into CPT row groups; every
+// thread owns CPT candidates (register blocking: the per-row constants are read from shared memory once
+// per CPT kernel evaluations) and every row group takes every CPT-th training row.  Training rows are
+// staged through shared memory as records [x (NXB) | C columns (NCB)], zero padded, so the inner loops
+// have compile-time bounds and no predicates.
+//   MODE 0: acc[c] += kx * C[c][i]; panel[a][i][t] = kx * G[a][i]        (swizzled for the DMMA kernel)
+//   MODE 1: acc[c] += beta[i][t] * kx * H[c][i]                           (second variance derivative)
+#pragma once
+#include "common.cuh"
+#include "exp2_table.h"
+
+namespace gpd {
+
+// exp(t) for t <= 0, ~1e-16 relative: t = (m/64) ln2 + u, |u| <= ln2/128;  e^t = 2^(m>>6) * 2^((m&63)/64) * e^u
+// with a degree-5 Taylor polynomial for e^u (|error| < 4e-17) and a 64-entry table.  10 FP64 instructions
+// instead of the ~17 FP64 + ~10 integer instructions of the library exp().
+__device__ __forceinline__ double exp_neg_fast(double t, const double* __restrict__ tab) {
+    const double kMagic = 6755399441055744.0;          // 1.5 * 2^52: the FMA rounds t*64/ln2 to an integer
+    const double z = fma(t, 92.33248261689366, kMagic);
+    const int m = __double2loint(z);
+    const double zr = z - kMagic;
+    double u = fma(zr, -0.01083042469326756, t);       // ln2/64 high part (m * hi is exact)
+    u = fma(zr, -2.9815858269852933e-12, u);           // low part
+    double p = fma(u, 1.0 / 120.0, 1.0 / 24.0);
+    p = fma(p, u, 1.0 / 6.0);
+    p = fma(p, u, 0.5);
+    p = fma(p, u, 1.0);
+    p = fma(p, u, 1.0);
+    const double r = tab[m & 63] * p;
+    const double s = __hiloint2double(__double2hiint(r) + ((m >> 6) << 20), __double2loint(r));
+    return t < -700.0 ? 0.0 : s;
+}
+
+template <int KERN>
+__device__ __forceinline__ double kappa_of_r2(double r2, double power, const double* __restrict__ tab) {
+    if (KERN == 0) return exp_neg_fast(-0.5 * r2, tab);          // RBF: exp(-r^2/2)
+    double r = sqrt(r2);
+    if (KERN == 1) return exp(-r);                               // Exponential
+    if (KERN == 2) {                                             // Matern32
+        const double s3 = 1.7320508075688772;
+        return (1.0 + s3 * r) * exp(-s3 * r);
+    }
+    if (KERN == 3) {                                             // Matern52
+        const double s5 = 2.23606797749979;
+        return (1.0 + s5 * r + 5.0 / 3.0 * (r * r)) * exp(-s5 * r);
+    }
+    if (KERN == 4) return cos(r);                                // Cosine
+    return exp(-power * log1p(0.5 * r2));                        // RatQuad
+}
+
+constexpr int kEvalThreads = 128;
+
+template <int NXB, int NCB, int CPT, int MODE>
+struct EvalSmem {
+    static constexpr int kRows = (NCB > 28) ? 32 : 64;           // training rows per shared-memory stage
+    static constexpr int RS = (NXB + NCB + 1) & ~1;              // record stride, even (16-byte vector loads)
+    static constexpr int kRec = kRows * RS;
+    static constexpr int kG = (MODE == 0) ? kRows * (kMaxP + 1) : 0;
+    static constexpr int kRed = (CPT > 1) ? kBlk * NCB : 0;
+    static constexpr int kMain = kRec + kG;
+    static constexpr int kDoubles = (kMain > kRed ? kMain : kRed) + 64;
+};
+
+template <int KERN, int NXB, int NCB, int CPT, int MODE, bool ONE_RHS>
+__global__ void __launch_bounds__(kEvalThreads, (CPT == 4 && NCB <= 8) ? 4 : 1) eval_kernel(const GpView* __restrict__ gps, const Item* __restrict__ items,
+                                                            const double* __restrict__ X, int ldx, int chunk_n, int nrhs,
+                                                            int ncols, double* __restrict__ panels,
+                                                            const double* __restrict__ beta_panels,
+                                                            const RawOut* __restrict__ raws, int ldraw) {
+    using SM = EvalSmem<NXB, NCB, CPT, MODE>;
+    constexpr int RS = SM::RS;
+    constexpr int kEvalRows = SM::kRows;
+    constexpr int TPG = kEvalThreads / CPT;                      // threads per row group
+    __shared__ __align__(16) double smem[SM::kDoubles];
+    double* sRec = smem;
+    double* sG = smem + SM::kRec;
+    double* sRed = smem;                                         // reused after the main loop
+    double* sTab = smem + (SM::kDoubles - 64);
+
+    const Item it = items[blockIdx.x];
+    const GpView& g = gps[it.gp];
+    const int count = g.count ? *g.count : chunk_n;
+    const int slot0 = it.tile * kBlk;
+    if (slot0 >= count) return;
+    const int tid = threadIdx.x;
+    const int rg = tid / TPG, s = tid % TPG;
+    const int n_pad = g.n_pad, nx = g.nx;
+    const double power = g.power_x;
+    if (KERN == 0 && tid < 64) sTab[tid] = kExp2Tab[tid];
+
+    double xs[CPT][NXB];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+        const int slot = slot0 + s + j * TPG;
+        const bool valid = slot < count;
+        const int cand = valid ? (g.idx ? g.idx[slot] : slot) : 0;
+#pragma unroll
+        for (int d = 0; d < NXB; ++d) {
+            double v = 0.0;
+            if (d < nx && valid) {
+                const double x = X[(size_t)cand * ldx + g.x_active[d]];
+                v = ((x - g.xmin[d]) / g.xdiff[d]) / g.ls[d];   // trans_x, then GPy's X / lengthscale
+            }
+            xs[j][d] = v;
+        }
+    }
+    double acc[CPT][NCB];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j)
+#pragma unroll
+        for (int c = 0; c < NCB; ++c) acc[j][c] = 0.0;
+
+    const double* __restrict__ gX = g.Xs;
+    const double* __restrict__ gC = (MODE == 0) ? g.C : g.H;
+    const double* __restrict__ gG = g.G;
+    double* __restrict__ pan = nullptr;
+    const double* __restrict__ bpan = nullptr;
+    if (MODE == 0) pan = panels + g.panel_off * nrhs + (size_t)it.tile * nrhs * n_pad * kBlk;
+    else bpan = beta_panels + g.panel_off + (size_t)it.tile * n_pad * kBlk;   // beta panels hold one RHS kind
+
+    for (int i0 = 0; i0 < n_pad; i0 += kEvalRows) {
+        __syncthreads();
+        for (int k = tid; k < kEvalRows * NXB; k += kEvalThreads) {
+            const int row = k / NXB, d = k % NXB;
+            sRec[row * RS + d] = (d < nx) ? gX[(size_t)(i0 + row) * nx + d] : 0.0;
+        }
+        for (int k = tid; k < kEvalRows * NCB; k += kEvalThreads) {
+            const int c = k / kEvalRows, row = k % kEvalRows;
+            sRec[row * RS + NXB + c] = (c < ncols) ? gC[(size_t)c * n_pad + i0 + row] : 0.0;
+        }
+        if (MODE == 0) {
+            for (int k = tid; k < kEvalRows * nrhs; k += kEvalThreads) {
+                const int a = k / kEvalRows, row = k % kEvalRows;
+                sG[a * kEvalRows + row] = gG[(size_t)a * n_pad + i0 + row];
+            }
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int ii = rg; ii < kEvalRows; ii += CPT) {
+            const double* __restrict__ rec = sRec + ii * RS;
+            double xr[NXB], cr[NCB];
+#pragma unroll
+            for (int d = 0; d < NXB; d += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(rec + d);
+                xr[d] = v.x;
+                xr[d + 1] = v.y;
+            }
+#pragma unroll
+            for (int c = 0; c < NCB; ++c) cr[c] = rec[NXB + c];
+            const int row = i0 + ii;
+            const int sw = (row & 3) << 2;
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                double r2 = 0.0;
+#pragma unroll
+                for (int d = 0; d < NXB; ++d) {
+                    const double df = xs[j][d] - xr[d];
+                    r2 = fma(df, df, r2);
+                }
+                double kap = kappa_of_r2<KERN>(r2, power, sTab);
+                const int t = (s + j * TPG) ^ sw;
+                if (MODE == 1) kap *= bpan[(size_t)row * kBlk + t];
+#pragma unroll
+                for (int c = 0; c < NCB; ++c) acc[j][c] = fma(kap, cr[c], acc[j][c]);
+                if (MODE == 0) {
+                    if (ONE_RHS) {
+                        pan[(size_t)row * kBlk + t] = kap * sG[ii];
+                    } else {
+                        for (int a = 0; a < nrhs; ++a)
+                            pan[((size_t)a * n_pad + row) * kBlk + t] = kap * sG[a * kEvalRows + ii];
+                    }
+                }
+            }
+        }
+    }
+    // ---- combine the row groups (group 0 accumulates), then write the raw contractions ----
+    if (CPT > 1) {
+#pragma unroll 1
+        for (int gsrc = 1; gsrc < CPT; ++gsrc) {
+            __syncthreads();
+            if (rg == gsrc) {
+#pragma unroll
+                for (int j = 0; j < CPT; ++j)
+#pragma unroll
+                    for (int c = 0; c < NCB; ++c) sRed[(s + j * TPG) * NCB + c] = acc[j][c];
+            }
+            __syncthreads();
+            if (rg == 0) {
+#pragma unroll
+                for (int j = 0; j < CPT; ++j)
+#pragma unroll
+                    for (int c = 0; c < NCB; ++c) acc[j][c] += sRed[(s + j * TPG) * NCB + c];
+            }
+        }
+    }
+    if (rg != 0) return;
+    const RawOut& raw = raws[g.model];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+        const int slot = slot0 + s + j * TPG;
+        if (slot >= count) continue;
+        const int cand = g.idx ? g.idx[slot] : slot;
+        const size_t orow = (size_t)g.out_e * chunk_n + cand;
+        if (MODE == 0) {
+#pragma unroll
+            for (int c = 0; c < NCB; ++c)
+                if (c < ncols) raw.cmu[orow * ldraw + c] = acc[j][c];
+            raw.kss[orow] = g.kss;
+        } else {
+            const int np = g.P * (g.P + 1) / 2;
+#pragma unroll
+            for (int c = 0; c < NCB; ++c)
+                if (c < ncols) raw.bh[orow * np + c] = acc[j][c];
+        }
+    }
+}
+
+// ---- bucket dispatch: NXB in {2,4,8}; MODE 0 column buckets {2,5,8,11,17,28,72}; MODE 1 {3,10,28,55} ----
+template <int KERN, int NXB, int NCB, int CPT, int MODE>
+static int launch_one(cudaStream_t s, int nitems, int ncols, const GpView* gps, const Item* items, const double* X,
+                      int ldx, int chunk_n, int nrhs, double* panels, const double* beta, const RawOut* raws,
+                      int ldraw) {
+    if (MODE == 0 && nrhs == 1 && NCB <= 17)
+        eval_kernel<KERN, NXB, NCB, CPT, MODE, true><<<nitems, kEvalThreads, 0, s>>>(gps, items, X, ldx, chunk_n, nrhs, ncols,
+                                                                                     panels, beta, raws, ldraw);
+    else
+        eval_kernel<KERN, NXB, NCB, CPT, MODE, false><<<nitems, kEvalThreads, 0, s>>>(gps, items, X, ldx, chunk_n, nrhs, ncols,
+                                                                                      panels, beta, raws, ldraw);
+    GPD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int KERN, int NXB>
+static int dispatch_cols(cudaStream_t s, int mode, int nitems, int ncols, const GpView* gps, const Item* items,
+                         const double* X, int ldx, int chunk_n, int nrhs, double* panels, const double* beta,
+                         const RawOut* raws, int ldraw) {
+#define GPD_GO(NCB, CPT, MODE) \
+    return launch_one<KERN, NXB, NCB, CPT, MODE>(s, nitems, ncols, gps, items, X, ldx, chunk_n, nrhs, panels, beta, raws, ldraw)
+    if (mode == 0) {
+        if (ncols <= 2) GPD_GO(2, 4, 0);
+        if (ncols <= 5) GPD_GO(5, 4, 0);
+        if (ncols <= 8) GPD_GO(8, 4, 0);
+        if (ncols <= 11) GPD_GO(11, 4, 0);
+        if (ncols <= 17) GPD_GO(17, 2, 0);
+        if (ncols <= 28) GPD_GO(28, 2, 0);
+        if (ncols <= 72) GPD_GO(72, 1, 0);
+        set_error("evaluation kernel supports at most 72 coefficient columns (P <= 10 for second order)");
+        return 3;
+    }
+    if (ncols <= 3) GPD_GO(3, 4, 1);
+    if (ncols <= 10) GPD_GO(10, 4, 1);
+    if (ncols <= 28) GPD_GO(28, 2, 1);
+    if (ncols <= 55) GPD_GO(55, 1, 1);
+    set_error("second variance derivative supports P <= 10 model parameters");
+    return 3;
+#undef GPD_GO
+}
+
+template <int KERN>
+static int dispatch_nx(cudaStream_t s, int mode, int nitems, int ncols, int nx, const GpView* gps, const Item* items,
+                       const double* X, int ldx, int chunk_n, int nrhs, double* panels, const double* beta,
+                       const RawOut* raws, int ldraw) {
+    if (nx <= 2) return dispatch_cols<KERN, 2>(s, mode, nitems, ncols, gps, items, X, ldx, chunk_n, nrhs, panels, beta, raws, ldraw);
+    if (nx <= 4) return dispatch_cols<KERN, 4>(s, mode, nitems, ncols, gps, items, X, ldx, chunk_n, nrhs, panels, beta, raws, ldraw);
+    if (nx <= 8) return dispatch_cols<KERN, 8>(s, mode, nitems, ncols, gps, items, X, ldx, chunk_n, nrhs, panels, beta, raws, ldraw);
+    set_error("x-kernel acts on 1..8 non-binary design dimensions");
+    return 3;
+}
+
+#define GPD_DEFINE_EVAL_TU(K)                                                                                  \
+    int launch_eval_k##K(cudaStream_t s, int mode, int nitems, int ncols, int nx, const GpView* gps,            \
+                         const Item* items, const double* X, int ldx, int chunk_n, int nrhs, double* panels,   \
+                         const double* beta, const RawOut* raws, int ldraw) {                                  \
+        return dispatch_nx<K>(s, mode, nitems, ncols, nx, gps, items, X, ldx, chunk_n, nrhs, panels, beta, raws, ldraw); \
+    }
+
+}  // namespace gpd

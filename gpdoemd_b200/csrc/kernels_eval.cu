@@ -8,6 +8,7 @@
 // (surrogate_model.py:175, :105), kp(p*,P_i) and its p-derivatives are candidate independent.  K0
 // folds them, alpha and the x-variance into column-major coefficient tables; K1 then needs a single
 // transcendental per (candidate, training point).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace gpd {
@@ -59,23 +60,6 @@ __device__ __forceinline__ void radial_profile(int kernel, double r, double powe
             d2k = dr1 + dr2;
         } break;
     }
-}
-
-template <int KERN>
-__device__ __forceinline__ double kappa_of_r2(double r2, double power) {
-    if (KERN == 0) return exp(-0.5 * r2);
-    double r = sqrt(r2);
-    if (KERN == 1) return exp(-r);
-    if (KERN == 2) {
-        const double s3 = 1.7320508075688772;
-        return (1.0 + s3 * r) * exp(-s3 * r);
-    }
-    if (KERN == 3) {
-        const double s5 = 2.23606797749979;
-        return (1.0 + s5 * r + 5.0 / 3.0 * (r * r)) * exp(-s5 * r);
-    }
-    if (KERN == 4) return cos(r);
-    return exp(-power * log1p(0.5 * r2));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -141,183 +125,44 @@ int launch_pstate(cudaStream_t s, int kernel, int n, int n_pad, int P, int dim_z
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1: one thread per candidate of a 128-wide tile, training rows staged through shared memory.
-//   MODE 0: acc[c] += kx * C[c][i]            and write RHS panels  kx * G[a][i]  (swizzled, layout.h)
-//   MODE 1: acc[c] += beta[i][t] * kx * H[c][i]   (second-order variance term, beta read from a panel)
+// K1 dispatch: the kernel template lives in eval_impl.cuh and is instantiated per kernel class in
+// eval_k0.cu .. eval_k5.cu (parallel compilation).
 // ---------------------------------------------------------------------------------------------
-constexpr int kEvalRows = 32;   // training rows per shared-memory stage
+#define GPD_DECL_K(K)                                                                                          \
+    int launch_eval_k##K(cudaStream_t s, int mode, int nitems, int ncols, int nx, const GpView* gps,            \
+                         const Item* items, const double* X, int ldx, int chunk_n, int nrhs, double* panels,   \
+                         const double* beta, const RawOut* raws, int ldraw);
+GPD_DECL_K(0) GPD_DECL_K(1) GPD_DECL_K(2) GPD_DECL_K(3) GPD_DECL_K(4) GPD_DECL_K(5)
+#undef GPD_DECL_K
 
-template <int KERN, int NX, int NCB, int MODE>
-__global__ void __launch_bounds__(kBlk) eval_kernel(const GpView* __restrict__ gps, const Item* __restrict__ items,
-                                                    const double* __restrict__ X, int ldx, int chunk_n, int nrhs,
-                                                    int ncols, double* __restrict__ panels,
-                                                    const double* __restrict__ beta_panels,
-                                                    const RawOut* __restrict__ raws, int ldraw) {
-    __shared__ double sX[kEvalRows * NX];
-    __shared__ double sC[NCB * kEvalRows];
-    __shared__ double sG[(MODE == 0 ? (1 + kMaxP) : 1) * kEvalRows];
-
-    const Item it = items[blockIdx.x];
-    const GpView& g = gps[it.gp];
-    const int count = g.count ? *g.count : chunk_n;
-    const int slot0 = it.tile * kBlk;
-    if (slot0 >= count) return;
-    const int t = threadIdx.x;
-    const int slot = slot0 + t;
-    const bool valid = slot < count;
-    const int cand = valid ? (g.idx ? g.idx[slot] : slot) : 0;
-    const int n_pad = g.n_pad;
-    const double power = g.power_x;
-
-    double xs[NX];
-#pragma unroll
-    for (int d = 0; d < NX; ++d) {
-        double x = valid ? X[(size_t)cand * ldx + g.x_active[d]] : 0.0;
-        xs[d] = ((x - g.xmin[d]) / g.xdiff[d]) / g.ls[d];   // trans_x, then GPy's X / lengthscale
-    }
-    double acc[NCB];
-#pragma unroll
-    for (int c = 0; c < NCB; ++c) acc[c] = 0.0;
-
-    const double* __restrict__ gX = g.Xs;
-    const double* __restrict__ gC = (MODE == 0) ? g.C : g.H;
-    const double* __restrict__ gG = g.G;
-    double* __restrict__ pan = nullptr;
-    const double* __restrict__ bpan = nullptr;
-    if (MODE == 0) pan = panels + g.panel_off * nrhs + (size_t)it.tile * nrhs * n_pad * kBlk;
-    else bpan = beta_panels + g.panel_off + (size_t)it.tile * n_pad * kBlk;   // beta panels hold one RHS kind
-
-    for (int i0 = 0; i0 < n_pad; i0 += kEvalRows) {
-        __syncthreads();
-        for (int k = t; k < kEvalRows * NX; k += kBlk) sX[k] = gX[(size_t)i0 * NX + k];
-        for (int k = t; k < ncols * kEvalRows; k += kBlk) {
-            int c = k / kEvalRows, i = k % kEvalRows;
-            sC[k] = gC[(size_t)c * n_pad + i0 + i];
-        }
-        if (MODE == 0) {
-            for (int k = t; k < nrhs * kEvalRows; k += kBlk) {
-                int a = k / kEvalRows, i = k % kEvalRows;
-                sG[k] = gG[(size_t)a * n_pad + i0 + i];
-            }
-        }
-        __syncthreads();
-#pragma unroll 2
-        for (int i = 0; i < kEvalRows; ++i) {
-            double r2 = 0.0;
-#pragma unroll
-            for (int d = 0; d < NX; ++d) {
-                double df = xs[d] - sX[i * NX + d];
-                r2 = fma(df, df, r2);
-            }
-            double kap = kappa_of_r2<KERN>(r2, power);
-            const int row = i0 + i;
-            if (MODE == 1) kap *= bpan[(size_t)row * kBlk + (t ^ ((row & 3) << 2))];
-#pragma unroll
-            for (int c = 0; c < NCB; ++c)
-                if (c < ncols) acc[c] = fma(kap, sC[c * kEvalRows + i], acc[c]);
-            if (MODE == 0) {
-                for (int a = 0; a < nrhs; ++a)
-                    pan[((size_t)a * n_pad + row) * kBlk + (t ^ ((row & 3) << 2))] = kap * sG[a * kEvalRows + i];
-            }
-        }
-    }
-    if (!valid) return;
-    const RawOut& raw = raws[g.model];
-    const size_t orow = (size_t)g.out_e * chunk_n + cand;
-    if (MODE == 0) {
-#pragma unroll
-        for (int c = 0; c < NCB; ++c)
-            if (c < ncols) raw.cmu[orow * ldraw + c] = acc[c];
-        raw.kss[orow] = g.kss;
-    } else {
-        const int np = g.P * (g.P + 1) / 2;
-#pragma unroll
-        for (int c = 0; c < NCB; ++c)
-            if (c < ncols) raw.bh[orow * np + c] = acc[c];
-    }
-}
-
-template <int KERN, int NX, int MODE>
-static int dispatch_ncb(cudaStream_t s, int nitems, int ncols, const GpView* gps, const Item* items,
-                        const double* X, int ldx, int chunk_n, int nrhs, double* panels, const double* beta,
-                        const RawOut* raws, int ldraw) {
-    if (ncols <= 8)
-        eval_kernel<KERN, NX, 8, MODE><<<nitems, kBlk, 0, s>>>(gps, items, X, ldx, chunk_n, nrhs, ncols, panels,
-                                                                beta, raws, ldraw);
-    else if (ncols <= 24)
-        eval_kernel<KERN, NX, 24, MODE><<<nitems, kBlk, 0, s>>>(gps, items, X, ldx, chunk_n, nrhs, ncols, panels,
-                                                                 beta, raws, ldraw);
-    else if (ncols <= 72)
-        eval_kernel<KERN, NX, 72, MODE><<<nitems, kBlk, 0, s>>>(gps, items, X, ldx, chunk_n, nrhs, ncols, panels,
-                                                                 beta, raws, ldraw);
-    else {
-        set_error("evaluation kernel supports at most 72 coefficient columns (P <= 10 for second order)");
-        return 3;
-    }
-    GPD_CUDA(cudaGetLastError());
-    return 0;
-}
-
-template <int KERN, int MODE>
-static int dispatch_nx(cudaStream_t s, int nx, int nitems, int ncols, const GpView* gps, const Item* items,
-                       const double* X, int ldx, int chunk_n, int nrhs, double* panels, const double* beta,
-                       const RawOut* raws, int ldraw) {
-#define GPD_NX_CASE(NXV)                                                                                   \
-    case NXV:                                                                                              \
-        return dispatch_ncb<KERN, NXV, MODE>(s, nitems, ncols, gps, items, X, ldx, chunk_n, nrhs, panels,  \
-                                             beta, raws, ldraw);
-    switch (nx) {
-        GPD_NX_CASE(1)
-        GPD_NX_CASE(2)
-        GPD_NX_CASE(3)
-        GPD_NX_CASE(4)
-        GPD_NX_CASE(5)
-        GPD_NX_CASE(6)
-        GPD_NX_CASE(7)
-        GPD_NX_CASE(8)
-        default:
-            set_error("x-kernel acts on 1..8 non-binary design dimensions");
-            return 3;
-    }
-#undef GPD_NX_CASE
-}
-
-template <int MODE>
-static int dispatch_kernel(cudaStream_t s, int kernel, int nx, int nitems, int ncols, const GpView* gps,
+static int dispatch_kernel(cudaStream_t s, int mode, int kernel, int nx, int nitems, int ncols, const GpView* gps,
                            const Item* items, const double* X, int ldx, int chunk_n, int nrhs, double* panels,
                            const double* beta, const RawOut* raws, int ldraw) {
-#define GPD_K_CASE(KV)                                                                                     \
-    case KV:                                                                                               \
-        return dispatch_nx<KV, MODE>(s, nx, nitems, ncols, gps, items, X, ldx, chunk_n, nrhs, panels, beta, \
-                                     raws, ldraw);
     switch (kernel) {
-        GPD_K_CASE(0)
-        GPD_K_CASE(1)
-        GPD_K_CASE(2)
-        GPD_K_CASE(3)
-        GPD_K_CASE(4)
-        GPD_K_CASE(5)
+#define GPD_K_CASE(K) \
+    case K: return launch_eval_k##K(s, mode, nitems, ncols, nx, gps, items, X, ldx, chunk_n, nrhs, panels, beta, raws, ldraw);
+        GPD_K_CASE(0) GPD_K_CASE(1) GPD_K_CASE(2) GPD_K_CASE(3) GPD_K_CASE(4) GPD_K_CASE(5)
+#undef GPD_K_CASE
         default:
             set_error("unknown kernel id");
             return 3;
     }
-#undef GPD_K_CASE
 }
 
 int launch_eval(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int nitems, const double* X_dev,
                 int ldx, int chunk_n, int nrhs, int ncols, int kernel, int nx, double* scratch,
                 const RawOut* raw_dev, int ldraw) {
     if (nitems == 0) return 0;
-    return dispatch_kernel<0>(s, kernel, nx, nitems, ncols, gps_dev, items_dev, X_dev, ldx, chunk_n, nrhs, scratch,
-                              nullptr, raw_dev, ldraw);
+    return dispatch_kernel(s, 0, kernel, nx, nitems, ncols, gps_dev, items_dev, X_dev, ldx, chunk_n, nrhs, scratch,
+                           nullptr, raw_dev, ldraw);
 }
 
 int launch_beta_contract(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int nitems,
                          const double* X_dev, int ldx, int chunk_n, int kernel, int nx, int P,
                          const double* beta_panels, const RawOut* raw_dev) {
     if (nitems == 0) return 0;
-    return dispatch_kernel<1>(s, kernel, nx, nitems, P * (P + 1) / 2, gps_dev, items_dev, X_dev, ldx, chunk_n,
-                              1, nullptr, beta_panels, raw_dev, 0);
+    return dispatch_kernel(s, 1, kernel, nx, nitems, P * (P + 1) / 2, gps_dev, items_dev, X_dev, ldx, chunk_n, 1,
+                           nullptr, beta_panels, raw_dev, 0);
 }
 
 }  // namespace gpd
