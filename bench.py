@@ -256,9 +256,16 @@ def main():
     tri_ms = tri['ms'] / max(1, tri['launches'])
     achieved = tri['flops'] / max(tri['launches'], 1) / (tri_ms * 1e-3) / 1e12 if tri['launches'] else None
     gpu_ms = sum(v['ms'] for v in prof.values())
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
+        if args.config in tj and not args.candidates:
+            traffic = tj[args.config]['dram_bytes_read'] + tj[args.config]['dram_bytes_write']
+    except Exception:
+        pass
     roofline = {'bound': 'tensor', 'kernel': 'tri_kernel (FP64 DMMA triangular contraction V = L^-1 K*)',
                 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak if achieved else None,
-                'traffic': None,
+                'traffic': traffic,
                 'peak_source': 'FP64 mma.sync m8n8k4 register-resident probe run in this process (MEASURED_PEAKS.json '
                                'has no FP64 entry; cuBLAS DGEMM on this pool: 36.1 TFLOP/s, profiles/r01_fp64_peak.jsonl)',
                 'algorithmic_flops_per_launch': tri['flops'] / max(tri['launches'], 1),
