@@ -127,6 +127,14 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--tri-variant', type=int, default=None)
     args = ap.parse_args()
+    # ONE JSON line on stdout: libraries (NCCL prints its version banner there) are sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+
+    def emit(line):
+        real_stdout.write(json.dumps(line) + '\n')
+        real_stdout.flush()
 
     from gpdoemd_b200 import synthetic
     cfg = dict(synthetic.CONFIGS[args.config])
@@ -151,7 +159,7 @@ def main():
                 'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
                                  'sample': '%d candidates per step of the same workload (all models, all criteria)' % ns},
                 'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -282,14 +290,14 @@ def main():
     if e2e_ms is not None:
         nk = len(crits)
         line['e2e'] = {'value': N * world / (e2e_ms / args.steps * 1e-3), 'unit': UNIT,
-                       'h2d_bytes_per_step': N * D * 8, 'd2h_bytes_per_step': nk * (N * 8 + 16),
+                       'h2d_bytes_per_step': world * N * D * 8, 'd2h_bytes_per_step': world * nk * (N * 8 + 16),
                        'api': 'gpdoemd_b200.score_designs_multi(models, X_host_pinned, criteria) -> dc arrays + argmax'}
     if not args.no_cpu_baseline and world >= 1:
         ns = cpu_sample_size(cfg)[args.config]
         v, sps = cpu_reference_run(cfg, seed, ns, 1, 0)
         line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
                                 'sample': '%d candidates of the same workload, 1 step, NumPy/LAPACK threads = all cores' % ns}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
