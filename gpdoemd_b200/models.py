@@ -514,7 +514,10 @@ class GPModel:
         return out
 
     def _predict(self, xnew, p):
-        h = self._hooks(xnew, p, ())
+        # the first p-derivative of the mean costs P extra FMAs per (candidate, training row) in the same
+        # pass, so it is computed eagerly: the reference's predict + per-output d_mu_d_p loop
+        # (taylor_first_order.py:29-33) then needs ONE device pass instead of two
+        h = self._hooks(xnew, p, ('dmu',))
         return h['mu'].copy(), h['s2'].copy()
 
     def _pstar(self):
