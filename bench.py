@@ -126,6 +126,7 @@ def main():
     ap.add_argument('--candidates', type=float, default=None, help='override N per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--tri-variant', type=int, default=None)
+    ap.add_argument('--tri-cps', type=int, default=None)
     args = ap.parse_args()
     # ONE JSON line on stdout: libraries (NCCL prints its version banner there) are sent to stderr
     sys.stdout.flush()
@@ -172,8 +173,10 @@ def main():
     ctx = g.get_context(local_rank)
     if args.tri_variant is not None:
         ctx.set_option('tri_variant', args.tri_variant)
+    if args.tri_cps is not None:
+        ctx.set_option('tri_cps', args.tri_cps)
     if cfg['n'] >= 2000:
-        ctx.set_scratch_bytes(24 << 30)
+        ctx.set_scratch_bytes(64 << 30)
 
     # ---- problem: identical GP state on every rank, candidates = this rank's contiguous shard ----------
     models, ds = synthetic.build_models(g.GPModel, seed, cfg['M'], cfg['E'], cfg['D'], cfg['P'], cfg['n'], cfg['kernel'],

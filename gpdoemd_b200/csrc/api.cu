@@ -55,6 +55,7 @@ struct gpd_ctx {
     DevBuf scratch, tables, flush;
     uint64_t launches = 0;
     int tri_variant = 0;
+    int tri_cps = 0;   // 0 = automatic (by factor size), 1 or 2 = forced chunks per pipeline stage
     // profiling: event pairs recorded without synchronising, resolved in gpd_profile_read
     int profile = 0;
     struct Span { cudaEvent_t a, b; int fam; };
@@ -239,7 +240,7 @@ static int plan_build(gpd_ctx* c, gpd_model* const* models, int M, int flags, lo
             }
         // raws + hook outputs, bytes per candidate
         const int ncols = ncols_for(flags, P);
-        const int ng = nrhs * (nrhs + 1) / 2;
+        const int ng = pl.need_W ? nrhs * (nrhs + 1) / 2 : 4;
         size_t d = (size_t)E * (ncols + 1 + ng + ((flags & WANT_D2S2) ? npair : 0));
         d += (size_t)E * 2;
         if (flags & WANT_DMU) d += (size_t)E * P;
@@ -261,10 +262,36 @@ static int plan_build(gpd_ctx* c, gpd_model* const* models, int M, int flags, lo
               "scratch limit too small for one 128-candidate tile of these models; raise gpd_set_scratch_bytes");
     long long chunk = (long long)((c->scratch_limit - fixed) / per_cand);
     chunk = chunk / kBlk * kBlk;
-    const long long want = (N + kBlk - 1) / kBlk * kBlk;
-    chunk = std::min(chunk, want);
     chunk = std::min<long long>(chunk, 1 << 22);
     GPD_CHECK(chunk >= kBlk, "scratch limit too small");
+    const long long want = (N + kBlk - 1) / kBlk * kBlk;
+    if (want <= chunk) {
+        chunk = want;
+    } else {
+        // Several chunks.  The triangular kernel is persistent over num_sms CTAs and every work item costs the same,
+        // so a chunk of t tiles takes ceil(t * GPs * RHS / num_sms) item-times forward (+ ceil(t * GPs / num_sms)
+        // for the backward pass of the second variance derivative).  Pick the tile count in the upper half of the
+        // capacity that minimises the total over all chunks including the remainder chunk.
+        const long long T = want / kBlk, tmax = chunk / kBlk, tmin = std::max<long long>(1, tmax / 2);
+        const long long S = c->num_sms, G = (long long)pl.entries.size(), R = pl.max_nrhs;
+        const bool bwd = (flags & WANT_D2S2) != 0;
+        auto cost = [&](long long t) -> double {
+            if (t <= 0) return 0.0;
+            double v = (double)((t * G * R + S - 1) / S);
+            if (bwd) v += (double)((t * G + S - 1) / S);
+            return v + 0.05;                       // per-chunk launch / pipeline fill overhead
+        };
+        double best = 1e300;
+        long long best_t = tmax;
+        for (long long t = tmax; t >= tmin; --t) {
+            const double total = (double)(T / t) * cost(t) + cost(T % t);
+            if (total < best - 1e-9) {
+                best = total;
+                best_t = t;
+            }
+        }
+        chunk = best_t * kBlk;
+    }
     pl.chunk = (int)chunk;
     pl.tiles = pl.chunk / kBlk;
     return 0;
@@ -282,7 +309,7 @@ static int plan_materialize(gpd_ctx* c, Plan& pl, Bump& bump) {
         const int nrhs = pl.need_W ? 1 + P : 1;
         ModelBufs& b = pl.mb[m];
         b.ldraw = ncols_for(pl.flags, P);
-        b.ng = nrhs * (nrhs + 1) / 2;
+        b.ng = pl.need_W ? nrhs * (nrhs + 1) / 2 : tri_row_groups(c->tri_variant);
         b.raw.cmu = bump.take<double>((size_t)E * Nc * b.ldraw);
         b.raw.kss = bump.take<double>((size_t)E * Nc);
         b.raw.gram = bump.take<double>((size_t)E * Nc * b.ng);
@@ -361,6 +388,15 @@ static int plan_materialize(gpd_ctx* c, Plan& pl, Bump& bump) {
     return 0;
 }
 
+// Pipeline-stage depth of tri_kernel.  Measured on B200 (profiles/r01_summary.md): small factors (C2, n_pad 512)
+// prefer 3 stages of 32 k, large ones (n_pad 4096) 4 stages of 16 k.
+static int tri_cps_for(const gpd_ctx* c, const Plan& pl) {
+    if (c->tri_cps) return c->tri_cps;
+    int max_nblk = 0;
+    for (const auto& en : pl.entries) max_nblk = std::max(max_nblk, en.gp->nblk);
+    return max_nblk <= 8 ? 2 : 1;
+}
+
 // run the GP part for one chunk of nc candidates (device X, row stride ldx); results in pl.mb[m]
 static int run_chunk(gpd_ctx* c, Plan& pl, const double* X_dev, int ldx, int nc) {
     cudaStream_t s = c->stream;
@@ -400,8 +436,8 @@ static int run_chunk(gpd_ctx* c, Plan& pl, const double* X_dev, int ldx, int nc)
     }
     if (!pl.need_W) {
         Span sp(c, F_TRI, 1, n2sum);
-        GPD_TRY(launch_tri(s, pl.views_dev, pl.items_dev, pl.nitems, 1, 1, 1, 0, pl.panels_in, nullptr, pl.raws_dev, 1, nc,
-                           c->num_sms, c->tri_variant));
+        GPD_TRY(launch_tri(s, pl.views_dev, pl.items_dev, pl.nitems, 1, 1, 1, 0, pl.panels_in, nullptr, pl.raws_dev,
+                           tri_row_groups(c->tri_variant), nc, c->num_sms, c->tri_variant, tri_cps_for(c, pl)));
     } else {
         for (auto& grp : pl.groups) {
             const int nrhs = 1 + grp.P;
@@ -415,7 +451,7 @@ static int run_chunk(gpd_ctx* c, Plan& pl, const double* X_dev, int ldx, int nc)
             {
                 Span sp(c, F_TRI, 1, fl);
                 GPD_TRY(launch_tri(s, pl.views_dev, pl.items_dev + grp.item_begin, grp.item_count, nrhs, nrhs, nrhs, 0,
-                                   pl.panels_in, pl.panels_out, nullptr, 0, nc, c->num_sms, c->tri_variant));
+                                   pl.panels_in, pl.panels_out, nullptr, 0, nc, c->num_sms, c->tri_variant, tri_cps_for(c, pl)));
             }
             {
                 Span sp(c, F_GRAM, 1, fl / (double)std::max(1, pl.entries[grp.entries[0]].gp->n) * (nrhs + 1));
@@ -426,7 +462,7 @@ static int run_chunk(gpd_ctx* c, Plan& pl, const double* X_dev, int ldx, int nc)
                 {
                     Span sp(c, F_TRI, 1, flb);
                     GPD_TRY(launch_tri(s, pl.views_dev, pl.items_dev + grp.item_begin, grp.item_count, 1, nrhs, 1, 1,
-                                       pl.panels_out, pl.panels_beta, nullptr, 0, nc, c->num_sms, c->tri_variant));
+                                       pl.panels_out, pl.panels_beta, nullptr, 0, nc, c->num_sms, c->tri_variant, tri_cps_for(c, pl)));
                 }
                 Span sp(c, F_EVAL, 1, 0);
                 GPD_TRY(launch_beta_contract(s, pl.views_dev, pl.items_dev + grp.item_begin, grp.item_count, X_dev, ldx, nc,
@@ -439,7 +475,8 @@ static int run_chunk(gpd_ctx* c, Plan& pl, const double* X_dev, int ldx, int nc)
         ModelBufs& b = pl.mb[m];
         Span sp(c, F_MARG, 1, 0);
         GPD_TRY(launch_finalize(s, mo->xf_dev + (pl.transformed ? 1 : 0), pl.raws_dev, m, mo->E, mo->P, nc, b.ldraw, pl.flags,
-                                pl.need_W ? 1 + mo->P : 1, b.mu, b.ldmu, b.s2, b.dmu, b.d2mu, b.ds2, b.d2s2));
+                                pl.need_W ? 1 + mo->P : 1, pl.need_W ? 0 : tri_row_groups(c->tri_variant), b.mu, b.ldmu,
+                                b.s2, b.dmu, b.d2mu, b.ds2, b.d2s2));
     }
     return 0;
 }
@@ -521,6 +558,11 @@ int gpd_set_option(gpd_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "tri_variant")) {
         GPD_CHECK(value == 0 || value == 1, "tri_variant is 0 (16 consumer warps) or 1 (8 consumer warps)");
         c->tri_variant = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "tri_cps")) {
+        GPD_CHECK(value >= 0 && value <= 2, "tri_cps is 0 (automatic), 1 or 2");
+        c->tri_cps = (int)value;
         return 0;
     }
     set_error(std::string("unknown option ") + name);

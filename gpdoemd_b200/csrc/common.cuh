@@ -96,7 +96,7 @@ int launch_invert_and_pack(cudaStream_t s, const double* L_dev, int n, int n_pad
                            double* packF, double* packB, uint64_t* launches);
 int launch_tri(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int nitems, int nwork_rhs,
                int in_stride, int out_stride, int backward, const double* panels_in, double* panels_out,
-               const RawOut* raw_dev, int ng, int chunk_n, int num_sms, int variant);
+               const RawOut* raw_dev, int ng, int chunk_n, int num_sms, int variant, int cps);
 int launch_gram(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int nitems, int nrhs,
                 const double* panels, const RawOut* raw_dev, int chunk_n);
 int launch_dmma_probe(cudaStream_t s, int num_sms, int iters, double* sink_dev);
@@ -104,8 +104,9 @@ int launch_dmma_probe(cudaStream_t s, int num_sms, int iters, double* sink_dev);
 int launch_route(cudaStream_t s, const double* X_dev, int ldx, int chunk_n, int nb, const int* bcols,
                  const int* weights, int ncombo, int* idx, int* counts, int idx_stride);
 int launch_finalize(cudaStream_t s, const ModelXform* xf_dev, const RawOut* raw_dev, int model_slot, int E, int P,
-                    int chunk_n, int ldraw, int flags, int nrhs, double* mu, int ldmu, double* s2, double* dmu,
-                    double* d2mu, double* ds2, double* d2s2);
+                    int chunk_n, int ldraw, int flags, int nrhs, int npart, double* mu, int ldmu, double* s2,
+                    double* dmu, double* d2mu, double* ds2, double* d2s2);
+int tri_row_groups(int variant);   // WM of the selected tri_kernel variant = number of ||v||^2 partials
 int launch_assemble(cudaStream_t s, int order, int N, int E, int P, double* mu, int ldmu, const double* s2,
                     const double* dmu, const double* d2mu, const double* d2s2, const double* Sigma_dev, double* S,
                     int ldS, double* tmpA, double* tmp_s2);

@@ -44,7 +44,7 @@ int launch_route(cudaStream_t s, const double* X_dev, int ldx, int chunk_n, int 
 __device__ __forceinline__ int gram_index(int NR, int a, int b) { return a * NR - a * (a - 1) / 2 + (b - a); }
 
 __global__ void finalize_kernel(const ModelXform* __restrict__ xf, const RawOut* __restrict__ raws, int model_slot,
-                                int chunk_n, int ldraw, int flags, int nrhs, double* __restrict__ mu, int ldmu,
+                                int chunk_n, int ldraw, int flags, int nrhs, int npart, double* __restrict__ mu, int ldmu,
                                 double* __restrict__ s2, double* __restrict__ dmu, double* __restrict__ d2mu,
                                 double* __restrict__ ds2, double* __restrict__ d2s2) {
     const int E = xf->E, P = xf->P;
@@ -55,10 +55,14 @@ __global__ void finalize_kernel(const ModelXform* __restrict__ xf, const RawOut*
     const size_t row = (size_t)e * chunk_n + n;
     const double* c = raw.cmu + row * ldraw;
     const double ystd = xf->ystd[e];
-    const int ng = nrhs * (nrhs + 1) / 2;
+    // first order: npart row-group partials of ||v||^2 from tri_kernel, added in a fixed order;
+    // otherwise the upper triangle of [v W]'[v W] from gram_kernel
+    const int ng = npart > 0 ? npart : nrhs * (nrhs + 1) / 2;
     const double* gr = raw.gram + row * ng;
+    double vv = gr[0];
+    for (int k = 1; k < npart; ++k) vv += gr[k];
     mu[(size_t)n * ldmu + e] = xf->ymean[e] + c[0] * ystd;                // transform.py:69-73 back=True
-    s2[(size_t)n * E + e] = (raw.kss[row] - gr[0]) * (ystd * ystd);      // k** - v'v  (GPy _raw_predict)
+    s2[(size_t)n * E + e] = (raw.kss[row] - vv) * (ystd * ystd);      // k** - v'v  (GPy _raw_predict)
     if (flags & 1) {                                                     // d_mu_d_p  surrogate_model.py:185-189
         double* o = dmu + ((size_t)n * E + e) * P;
         for (int a = 0; a < P; ++a) o[a] = c[1 + a] * ystd / xf->pdiff[a];
@@ -92,12 +96,12 @@ __global__ void finalize_kernel(const ModelXform* __restrict__ xf, const RawOut*
 }
 
 int launch_finalize(cudaStream_t s, const ModelXform* xf_dev, const RawOut* raw_dev, int model_slot, int E, int P,
-                    int chunk_n, int ldraw, int flags, int nrhs, double* mu, int ldmu, double* s2, double* dmu,
-                    double* d2mu, double* ds2, double* d2s2) {
+                    int chunk_n, int ldraw, int flags, int nrhs, int npart, double* mu, int ldmu, double* s2,
+                    double* dmu, double* d2mu, double* ds2, double* d2s2) {
     (void)P;
     long long total = (long long)chunk_n * E;
     finalize_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(xf_dev, raw_dev, model_slot, chunk_n, ldraw,
-                                                                    flags, nrhs, mu, ldmu, s2, dmu, d2mu, ds2, d2s2);
+                                                                    flags, nrhs, npart, mu, ldmu, s2, dmu, d2mu, ds2, d2s2);
     GPD_CUDA(cudaGetLastError());
     return 0;
 }

@@ -18,6 +18,12 @@
 
 namespace gpd {
 
+#ifndef GPD_TRI_CYCLIC
+#define GPD_TRI_CYCLIC 0
+#endif
+// 8-row block owned by (row group wm, slot mb): blocked (wm*MB + mb) or cyclic (mb*WM + wm)
+#define GPD_BLK(wm, mb, WM, MB) (GPD_TRI_CYCLIC ? ((mb) * (WM) + (wm)) : ((wm) * (MB) + (mb)))
+
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
 // ---------------------------------------------------------------------------------------------
@@ -63,15 +69,21 @@ __device__ __forceinline__ void consumer_bar(int nthreads) {
 // ---------------------------------------------------------------------------------------------
 // the persistent triangular-GEMM kernel
 // ---------------------------------------------------------------------------------------------
-constexpr int kStages = 4;
-constexpr uint32_t kChunkBytes = kChunkElems * sizeof(double);   // 16384
+// CPS = 16-k chunks per pipeline stage (consecutive chunks are contiguous in both operands):
+//   CPS 1: 4 stages x (16 KiB A + 16 KiB B)      CPS 2: 3 stages x (32 KiB A + 32 KiB B)
+template <int CPS>
+struct TriCfg {
+    static constexpr int kStages = (CPS == 1) ? 4 : 3;
+    static constexpr int kStageElems = kChunkElems * CPS;
+    static constexpr uint32_t kStageBytes = kStageElems * sizeof(double);
+};
 
+template <int CPS>
 struct TriSmem {
-    double A[kStages][kChunkElems];
-    double B[kStages][kChunkElems];
-    double colsum[4][kBlk];
-    unsigned long long full[kStages];
-    unsigned long long empty[kStages];
+    double A[TriCfg<CPS>::kStages][TriCfg<CPS>::kStageElems];
+    double B[TriCfg<CPS>::kStages][TriCfg<CPS>::kStageElems];
+    unsigned long long full[TriCfg<CPS>::kStages];
+    unsigned long long empty[TriCfg<CPS>::kStages];
 };
 
 struct TriArgs {
@@ -120,11 +132,11 @@ __device__ __forceinline__ void compute_chunk(const double* __restrict__ sA, con
     constexpr int MB = 16 / WM, NB = 16 / WN;
     const int lq = lane & 3, lr = lane >> 2;
     if (DIAG) {
-        // whole chunk zero for this warp's rows?  rows [wm*MB*8, (wm+1)*MB*8), k in [16c, 16c+16)
-        const int rlo = wm * MB * 8, rhi = rlo + MB * 8 - 1, klo = chunk_in_blk * kChunkK, khi = klo + kChunkK - 1;
+        // whole chunk zero for this warp's rows?  8-row blocks mb*WM + wm (cyclic), k in [16c, 16c+16)
+        const int rlo = GPD_BLK(wm, 0, WM, MB) * 8, rhi = GPD_BLK(wm, MB - 1, WM, MB) * 8 + 7, klo = chunk_in_blk * kChunkK, khi = klo + kChunkK - 1;
         if (BWD ? (khi < rlo) : (klo > rhi)) return;
     }
-    const double* __restrict__ pa = sA + ((wm * MB * 2) * 32 + lane) * 2;
+    const double* __restrict__ pa = sA + lane * 2;
     // b_index(k, t), k = ks*4 + lq, t = (wn*NB + nb)*8 + lr: the swizzle (k & 3) << 2 == lq << 2 flips bits 2..3 of t,
     // i.e. it depends on lr and on the parity of nb only -> two lane-constant bases, even and odd nb
     static_assert(NB % 2 == 0, "NB must be even");
@@ -134,7 +146,7 @@ __device__ __forceinline__ void compute_chunk(const double* __restrict__ sA, con
     for (int kp = 0; kp < 2; ++kp) {
         double2 a2[MB];
 #pragma unroll
-        for (int mb = 0; mb < MB; ++mb) a2[mb] = *reinterpret_cast<const double2*>(pa + (mb * 2 + kp) * 64);
+        for (int mb = 0; mb < MB; ++mb) a2[mb] = *reinterpret_cast<const double2*>(pa + (GPD_BLK(wm, mb, WM, MB) * 2 + kp) * 64);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int ks = kp * 2 + h;
@@ -145,8 +157,17 @@ __device__ __forceinline__ void compute_chunk(const double* __restrict__ sA, con
             for (int nb = 0; nb < NB; ++nb) b[nb] = ((nb & 1) ? pb1 : pb0)[ks * 4 * kBlk + (nb >> 1) * 16];
             if (DIAG) {
                 const int k0 = chunk_in_blk * kChunkK + ks * 4;
-                int v = (k0 >> 3) - wm * MB + (BWD ? 1 : 0);
-                v = v < 0 ? 0 : (v > MB ? MB : v);
+                // block mb*WM + wm holds rows >= its first row; forward (lower) needs block >= k0/8,
+                // backward (upper) block <= k0/8
+                int v;
+                if (GPD_TRI_CYCLIC) {
+                    const int d = (k0 >> 3) - wm;
+                    v = BWD ? (d < 0 ? 0 : d / WM + 1) : (d <= 0 ? 0 : (d + WM - 1) / WM);
+                } else {
+                    v = (k0 >> 3) - wm * MB + (BWD ? 1 : 0);
+                    v = v < 0 ? 0 : v;
+                }
+                v = v > MB ? MB : v;
                 kstep_bounded<MB, NB, BWD, 0>(v, acc, a, b);
             } else {
                 kstep<MB, NB, 0, MB>(acc, a, b);
@@ -188,18 +209,22 @@ __device__ __forceinline__ void stream_seek_item(ChunkStream& ps, const TriArgs&
     }
 }
 
-template <bool BWD>
-__device__ __forceinline__ void stream_issue(ChunkStream& ps, const TriArgs& args, int nwork, TriSmem& sm) {
+template <bool BWD, int CPS>
+__device__ __forceinline__ void stream_issue(ChunkStream& ps, const TriArgs& args, int nwork, TriSmem<CPS>& sm) {
+    constexpr int kStages = TriCfg<CPS>::kStages;
+    constexpr uint32_t kStageBytes = TriCfg<CPS>::kStageBytes;
+    constexpr int kCps = CPS;
     if (ps.w >= nwork) return;
     mbar_wait(smem_u32(&sm.empty[ps.stage]), ps.phase ^ 1);
     const uint32_t fb = smem_u32(&sm.full[ps.stage]);
-    mbar_expect_tx(fb, 2 * kChunkBytes);
+    mbar_expect_tx(fb, 2 * kStageBytes);
     const int kb = tile_run_kfirst(ps.I, BWD) + ps.q;
-    bulk_g2s(smem_u32(sm.A[ps.stage]), ps.A + (size_t)ps.j * kChunkElems, kChunkBytes, fb);
-    bulk_g2s(smem_u32(sm.B[ps.stage]), ps.B + ((size_t)kb * kBlk + ps.c * kChunkK) * kBlk, kChunkBytes, fb);
+    bulk_g2s(smem_u32(sm.A[ps.stage]), ps.A + (size_t)ps.j * kChunkElems, kStageBytes, fb);
+    bulk_g2s(smem_u32(sm.B[ps.stage]), ps.B + ((size_t)kb * kBlk + ps.c * kChunkK) * kBlk, kStageBytes, fb);
     if (++ps.stage == kStages) { ps.stage = 0; ps.phase ^= 1; }
-    ++ps.j;
-    if (++ps.c == kChunksPerBlk) {
+    ps.j += kCps;
+    ps.c += kCps;
+    if (ps.c == kChunksPerBlk) {
         ps.c = 0;
         if (++ps.q == ps.len) {
             ps.q = 0;
@@ -215,12 +240,14 @@ __device__ __forceinline__ void stream_issue(ChunkStream& ps, const TriArgs& arg
 
 // 16 (WM=4) or 8 (WM=2) warps, all of them DMMA consumers; no dedicated producer warp: the register file is
 // allocated in groups of 4 warps, so a 17th warp would cost every thread a quarter of its registers.
-template <int WM, int WN, bool BWD>
+template <int WM, int WN, bool BWD, int CPS>
 __global__ void __launch_bounds__(WM * WN * 32, 1) tri_kernel(const TriArgs args) {
     constexpr int NCW = WM * WN;            // consumer warps
+    constexpr int kStages = TriCfg<CPS>::kStages;
+    constexpr int kCps = CPS;
     constexpr int MB = 16 / WM, NB = 16 / WN;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    TriSmem& sm = *reinterpret_cast<TriSmem*>(smem_raw);
+    TriSmem<CPS>& sm = *reinterpret_cast<TriSmem<CPS>*>(smem_raw);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -230,7 +257,6 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) tri_kernel(const TriArgs args
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int k = threadIdx.x; k < 4 * kBlk; k += blockDim.x) (&sm.colsum[0][0])[k] = 0.0;
     __syncthreads();
 
     const int nwork = args.nitems * args.nwork_rhs;
@@ -245,12 +271,14 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) tri_kernel(const TriArgs args
     if (is_producer) {
         stream_seek_item<BWD>(ps, args, nwork);
 #pragma unroll 1
-        for (int k = 0; k < kStages - 1; ++k) stream_issue<BWD>(ps, args, nwork, sm);
+        for (int k = 0; k < kStages - 1; ++k) stream_issue<BWD, CPS>(ps, args, nwork, sm);
     }
     __syncwarp();
 
     // ===== consumers: DMMA over the chunk stream =====
-    const int wm = warp / WN, wn = warp % WN;       // warp w lives on SMSP w%4: every SMSP sees all row groups
+    // warp w lives on SMSP w%4 = wn: every SMSP sees all row groups.  Row group wm owns the 8-row blocks
+    // mb*WM + wm (cyclic), so the staircase of a diagonal tile is spread evenly over the warps.
+    const int wm = warp / WN, wn = warp % WN;
     const int lq = lane & 3, lr = lane >> 2;
     for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
         const Item it = args.items[w / args.nwork_rhs];
@@ -280,23 +308,26 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) tri_kernel(const TriArgs args
             for (int q = 0; q < len; ++q) {
                 const bool diag = (q == qdiag);
 #pragma unroll 1
-                for (int c = 0; c < kChunksPerBlk; ++c) {
+                for (int c = 0; c < kChunksPerBlk; c += kCps) {
                     mbar_wait(smem_u32(&sm.full[stage]), phase);
-                    if (diag)
-                        compute_chunk<WM, WN, true, BWD>(sm.A[stage], sm.B[stage], lane, wm, wn, c, acc);
-                    else
-                        compute_chunk<WM, WN, false, BWD>(sm.A[stage], sm.B[stage], lane, wm, wn, c, acc);
+#pragma unroll
+                    for (int cc = 0; cc < kCps; ++cc) {
+                        const double* sA = sm.A[stage] + cc * kChunkElems;
+                        const double* sB = sm.B[stage] + cc * kChunkElems;
+                        if (diag) compute_chunk<WM, WN, true, BWD>(sA, sB, lane, wm, wn, c + cc, acc);
+                        else compute_chunk<WM, WN, false, BWD>(sA, sB, lane, wm, wn, c + cc, acc);
+                    }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stage]));
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
-                    if (is_producer) stream_issue<BWD>(ps, args, nwork, sm);
+                    if (is_producer) stream_issue<BWD, CPS>(ps, args, nwork, sm);
                     __syncwarp();
                 }
             }
             // ---- epilogue of row block I: optional store of V, running column sums of squares ----
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb) {
-                const int i = I * kBlk + (wm * MB + mb) * 8 + lr;
+                const int i = I * kBlk + GPD_BLK(wm, mb, WM, MB) * 8 + lr;
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) {
                     const double v0 = acc[mb][nb][0], v1 = acc[mb][nb][1];
@@ -311,7 +342,10 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) tri_kernel(const TriArgs args
             }
         }
         if (args.raws) {
-            // reduce over the 8 lanes that own the same columns (lane bits 2..4), then over row groups
+            // ||v||^2 partial of this warp's rows: butterfly over the 8 lanes that own the same columns (lane
+            // bits 2..4), then lane lr publishes column pair (nb = lr/2, j = lr%2).  No CTA barrier: the WM
+            // row-group partials go to separate slots and are added in a fixed order by finalize_kernel.
+            double mine = 0.0;
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
@@ -320,42 +354,40 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) tri_kernel(const TriArgs args
                     s += __shfl_xor_sync(0xffffffffu, s, 4);
                     s += __shfl_xor_sync(0xffffffffu, s, 8);
                     s += __shfl_xor_sync(0xffffffffu, s, 16);
-                    if (lr == 0) sm.colsum[wm][(wn * NB + nb) * 8 + 2 * lq + j] = s;
+                    if (lr == nb * 2 + j) mine = s;
                 }
-            __syncthreads();
-            if (threadIdx.x < kBlk) {
-                const int t = threadIdx.x;
-                double tot = 0.0;
-#pragma unroll
-                for (int r = 0; r < WM; ++r) tot += sm.colsum[r][t];
+            if (lr < 2 * NB) {
+                const int t = (wn * NB + (lr >> 1)) * 8 + 2 * lq + (lr & 1);
                 const int slot = it.tile * kBlk + t;
                 if (slot < count) {
                     const int cand = g.idx ? g.idx[slot] : slot;
                     const RawOut& raw = args.raws[g.model];
-                    raw.gram[((size_t)g.out_e * args.chunk_n + cand) * args.ng] = tot;
+                    raw.gram[((size_t)g.out_e * args.chunk_n + cand) * args.ng + wm] = mine;
                 }
             }
-            __syncthreads();
         }
     }
 }
 
-static bool g_tri_attr_done = false;
-int tri_setup_attributes() {
-    if (g_tri_attr_done) return 0;
-    GPD_CUDA(cudaFuncSetAttribute(tri_kernel<4, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TriSmem)));
-    GPD_CUDA(cudaFuncSetAttribute(tri_kernel<4, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TriSmem)));
-    GPD_CUDA(cudaFuncSetAttribute(tri_kernel<2, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TriSmem)));
-    GPD_CUDA(cudaFuncSetAttribute(tri_kernel<2, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TriSmem)));
-    g_tri_attr_done = true;
+int tri_row_groups(int variant) { return variant == 1 ? 2 : 4; }
+
+template <int WM, int WN, bool BWD, int CPS>
+static int tri_launch_one(cudaStream_t s, int grid, const TriArgs& args) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        GPD_CUDA(cudaFuncSetAttribute(tri_kernel<WM, WN, BWD, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(TriSmem<CPS>)));
+        attr_done = true;
+    }
+    tri_kernel<WM, WN, BWD, CPS><<<grid, WM * WN * 32, sizeof(TriSmem<CPS>), s>>>(args);
+    GPD_CUDA(cudaGetLastError());
     return 0;
 }
 
 int launch_tri(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int nitems, int nwork_rhs,
                int in_stride, int out_stride, int backward, const double* panels_in, double* panels_out,
-               const RawOut* raw_dev, int ng, int chunk_n, int num_sms, int variant) {
+               const RawOut* raw_dev, int ng, int chunk_n, int num_sms, int variant, int cps) {
     if (nitems == 0) return 0;
-    GPD_TRY(tri_setup_attributes());
     TriArgs args;
     args.gps = gps_dev;
     args.items = items_dev;
@@ -371,15 +403,16 @@ int launch_tri(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int
     args.chunk_n = chunk_n;
     long long nwork = (long long)nitems * nwork_rhs;
     int grid = (int)(nwork < num_sms ? nwork : num_sms);
+#define GPD_TRI_GO(WM, BWD, CPS) return tri_launch_one<WM, 4, BWD, CPS>(s, grid, args)
     if (variant == 1) {
-        if (backward) tri_kernel<2, 4, true><<<grid, 2 * 4 * 32, sizeof(TriSmem), s>>>(args);
-        else tri_kernel<2, 4, false><<<grid, 2 * 4 * 32, sizeof(TriSmem), s>>>(args);
-    } else {
-        if (backward) tri_kernel<4, 4, true><<<grid, 4 * 4 * 32, sizeof(TriSmem), s>>>(args);
-        else tri_kernel<4, 4, false><<<grid, 4 * 4 * 32, sizeof(TriSmem), s>>>(args);
+        if (backward) { if (cps == 2) GPD_TRI_GO(2, true, 2); GPD_TRI_GO(2, true, 1); }
+        if (cps == 2) GPD_TRI_GO(2, false, 2);
+        GPD_TRI_GO(2, false, 1);
     }
-    GPD_CUDA(cudaGetLastError());
-    return 0;
+    if (backward) { if (cps == 2) GPD_TRI_GO(4, true, 2); GPD_TRI_GO(4, true, 1); }
+    if (cps == 2) GPD_TRI_GO(4, false, 2);
+    GPD_TRI_GO(4, false, 1);
+#undef GPD_TRI_GO
 }
 
 // ---------------------------------------------------------------------------------------------
