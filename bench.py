@@ -244,6 +244,28 @@ def main():
         for c in crits:
             assert res_e2e[c][0] == res[c][0], 'resident and end-to-end paths disagree on the argmax'
 
+    # the reference's own call pattern (demos/case_study.py:284-293) through the drop-in functions: one
+    # taylor_* call per model (host arrays in and out), then one call per criterion -- informational
+    stepwise_ms = None
+    if X_host is not None and N <= 2000000:
+        marg = g.taylor_first_order if order == 1 else g.taylor_second_order
+        E, Mn = cfg['E'], cfg['M']
+
+        def step_stepwise():
+            mu = np.empty((N, Mn, E))
+            S = np.empty((N, Mn, E, E))
+            for i, mo in enumerate(models):
+                mu[:, i], S[:, i] = marg(mo, X_host)
+            return {c: int(np.argmax(getattr(g, c)(mu, S, noise, None))) for c in crits}
+        r_sw = step_stepwise()
+        barrier()
+        t0 = time.perf_counter()
+        nsw = max(1, min(3, args.steps))
+        for _ in range(nsw):
+            r_sw = step_stepwise()
+        stepwise_ms = (time.perf_counter() - t0) * 1e3 / nsw
+        for c in crits:
+            assert r_sw[c] + first_row == res[c][0], 'drop-in functions and fused path disagree on the argmax'
     clocks = sampler.stop()      # sampled over warm-up + timed steps + end-to-end steps (all under load)
 
     # ---- multi-GPU: the only collective is the argmax all-gather; time = max over ranks -----------------
@@ -295,6 +317,10 @@ def main():
         line['e2e'] = {'value': N * world / (e2e_ms / args.steps * 1e-3), 'unit': UNIT,
                        'h2d_bytes_per_step': world * N * D * 8, 'd2h_bytes_per_step': world * nk * (N * 8 + 16),
                        'api': 'gpdoemd_b200.score_designs_multi(models, X_host_pinned, criteria) -> dc arrays + argmax'}
+    if stepwise_ms is not None:
+        line['e2e_stepwise'] = {'value': N / (stepwise_ms * 1e-3), 'unit': UNIT, 'per_rank': True,
+                                'api': 'taylor_*_order(model, X) per model + HR/BH/...(mu, S, noise) per criterion, '
+                                       'NumPy arrays in and out, host wall clock'}
     if not args.no_cpu_baseline and world >= 1:
         ns = cpu_sample_size(cfg)[args.config]
         v, sps = cpu_reference_run(cfg, seed, ns, 1, 0)

@@ -54,29 +54,36 @@ __device__ __forceinline__ double kappa_of_r2(double r2, double power, const dou
     return exp(-power * log1p(0.5 * r2));                        // RatQuad
 }
 
-constexpr int kEvalThreads = 128;
 
-template <int NXB, int NCB, int CPT, int MODE>
+// Candidate (column of the 128-wide tile) of slot j of thread s in a row group of TPG threads: adjacent pairs
+// (2s, 2s+1) so that one 16-byte store / load per pair serves the swizzled panels (the swizzle flips bits 2..3 only).
+template <int CPT, int TPG>
+__device__ __forceinline__ int eval_col(int s, int j) {
+    return (CPT == 1) ? s : 2 * s + (j & 1) + (j >> 1) * 2 * TPG;
+}
+
+template <int NXB, int NCB, int CPT, int RG, int MODE>
 struct EvalSmem {
     static constexpr int kRows = (NCB > 28) ? 32 : 64;           // training rows per shared-memory stage
     static constexpr int RS = (NXB + NCB + 1) & ~1;              // record stride, even (16-byte vector loads)
     static constexpr int kRec = kRows * RS;
     static constexpr int kG = (MODE == 0) ? kRows * (kMaxP + 1) : 0;
-    static constexpr int kRed = (CPT > 1) ? kBlk * NCB : 0;
+    static constexpr int kRed = (RG > 1) ? kBlk * NCB : 0;
     static constexpr int kMain = kRec + kG;
     static constexpr int kDoubles = (kMain > kRed ? kMain : kRed) + 64;
 };
 
-template <int KERN, int NXB, int NCB, int CPT, int MODE, bool ONE_RHS>
-__global__ void __launch_bounds__(kEvalThreads, (CPT == 4 && NCB <= 8) ? 4 : 1) eval_kernel(const GpView* __restrict__ gps, const Item* __restrict__ items,
+template <int KERN, int NXB, int NCB, int CPT, int RG, int MODE, bool ONE_RHS>
+__global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 512 : 1024) / (RG * (kBlk / CPT)) : 1) eval_kernel(const GpView* __restrict__ gps, const Item* __restrict__ items,
                                                             const double* __restrict__ X, int ldx, int chunk_n, int nrhs,
                                                             int ncols, double* __restrict__ panels,
                                                             const double* __restrict__ beta_panels,
                                                             const RawOut* __restrict__ raws, int ldraw) {
-    using SM = EvalSmem<NXB, NCB, CPT, MODE>;
+    using SM = EvalSmem<NXB, NCB, CPT, RG, MODE>;
     constexpr int RS = SM::RS;
     constexpr int kEvalRows = SM::kRows;
-    constexpr int TPG = kEvalThreads / CPT;                      // threads per row group
+    constexpr int TPG = kBlk / CPT;                              // threads per row group (each covers the 128 candidates)
+    constexpr int kEvalThreads = RG * TPG;
     __shared__ __align__(16) double smem[SM::kDoubles];
     double* sRec = smem;
     double* sG = smem + SM::kRec;
@@ -97,7 +104,7 @@ __global__ void __launch_bounds__(kEvalThreads, (CPT == 4 && NCB <= 8) ? 4 : 1) 
     double xs[CPT][NXB];
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
-        const int slot = slot0 + s + j * TPG;
+        const int slot = slot0 + eval_col<CPT, TPG>(s, j);
         const bool valid = slot < count;
         const int cand = valid ? (g.idx ? g.idx[slot] : slot) : 0;
 #pragma unroll
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(kEvalThreads, (CPT == 4 && NCB <= 8) ? 4 : 1) 
         }
         __syncthreads();
 #pragma unroll 2
-        for (int ii = rg; ii < kEvalRows; ii += CPT) {
+        for (int ii = rg; ii < kEvalRows; ii += RG) {
             const double* __restrict__ rec = sRec + ii * RS;
             double xr[NXB], cr[NCB];
 #pragma unroll
@@ -155,6 +162,7 @@ __global__ void __launch_bounds__(kEvalThreads, (CPT == 4 && NCB <= 8) ? 4 : 1) 
             for (int c = 0; c < NCB; ++c) cr[c] = rec[NXB + c];
             const int row = i0 + ii;
             const int sw = (row & 3) << 2;
+            double kap[CPT];
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
                 double r2 = 0.0;
@@ -163,39 +171,59 @@ __global__ void __launch_bounds__(kEvalThreads, (CPT == 4 && NCB <= 8) ? 4 : 1) 
                     const double df = xs[j][d] - xr[d];
                     r2 = fma(df, df, r2);
                 }
-                double kap = kappa_of_r2<KERN>(r2, power, sTab);
-                const int t = (s + j * TPG) ^ sw;
-                if (MODE == 1) kap *= bpan[(size_t)row * kBlk + t];
+                kap[j] = kappa_of_r2<KERN>(r2, power, sTab);
+            }
+            if (MODE == 1) {
+                const double* __restrict__ brow = bpan + (size_t)row * kBlk;
+                if (CPT == 1) {
+                    kap[0] *= brow[s ^ sw];
+                } else {
 #pragma unroll
-                for (int c = 0; c < NCB; ++c) acc[j][c] = fma(kap, cr[c], acc[j][c]);
-                if (MODE == 0) {
-                    if (ONE_RHS) {
-                        pan[(size_t)row * kBlk + t] = kap * sG[ii];
+                    for (int jp = 0; jp < CPT / 2; ++jp) {
+                        const double2 b2 = *reinterpret_cast<const double2*>(brow + (eval_col<CPT, TPG>(s, 2 * jp) ^ sw));
+                        kap[2 * jp] *= b2.x;
+                        kap[2 * jp + 1] *= b2.y;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < CPT; ++j)
+#pragma unroll
+                for (int c = 0; c < NCB; ++c) acc[j][c] = fma(kap[j], cr[c], acc[j][c]);
+            if (MODE == 0) {
+                const int na = ONE_RHS ? 1 : nrhs;
+                for (int a = 0; a < na; ++a) {
+                    const double ga = sG[a * kEvalRows + ii];
+                    double* __restrict__ prow = pan + ((size_t)a * n_pad + row) * kBlk;
+                    if (CPT == 1) {
+                        prow[s ^ sw] = kap[0] * ga;
                     } else {
-                        for (int a = 0; a < nrhs; ++a)
-                            pan[((size_t)a * n_pad + row) * kBlk + t] = kap * sG[a * kEvalRows + ii];
+#pragma unroll
+                        for (int jp = 0; jp < CPT / 2; ++jp)
+                            *reinterpret_cast<double2*>(prow + (eval_col<CPT, TPG>(s, 2 * jp) ^ sw)) =
+                                make_double2(kap[2 * jp] * ga, kap[2 * jp + 1] * ga);
                     }
                 }
             }
         }
     }
     // ---- combine the row groups (group 0 accumulates), then write the raw contractions ----
-    if (CPT > 1) {
+    if (RG > 1) {
 #pragma unroll 1
-        for (int gsrc = 1; gsrc < CPT; ++gsrc) {
+        for (int gsrc = 1; gsrc < RG; ++gsrc) {
             __syncthreads();
             if (rg == gsrc) {
 #pragma unroll
                 for (int j = 0; j < CPT; ++j)
 #pragma unroll
-                    for (int c = 0; c < NCB; ++c) sRed[(s + j * TPG) * NCB + c] = acc[j][c];
+                    for (int c = 0; c < NCB; ++c) sRed[eval_col<CPT, TPG>(s, j) * NCB + c] = acc[j][c];
             }
             __syncthreads();
             if (rg == 0) {
 #pragma unroll
                 for (int j = 0; j < CPT; ++j)
 #pragma unroll
-                    for (int c = 0; c < NCB; ++c) acc[j][c] += sRed[(s + j * TPG) * NCB + c];
+                    for (int c = 0; c < NCB; ++c) acc[j][c] += sRed[eval_col<CPT, TPG>(s, j) * NCB + c];
             }
         }
     }
@@ -203,7 +231,7 @@ __global__ void __launch_bounds__(kEvalThreads, (CPT == 4 && NCB <= 8) ? 4 : 1) 
     const RawOut& raw = raws[g.model];
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
-        const int slot = slot0 + s + j * TPG;
+        const int slot = slot0 + eval_col<CPT, TPG>(s, j);
         if (slot >= count) continue;
         const int cand = g.idx ? g.idx[slot] : slot;
         const size_t orow = (size_t)g.out_e * chunk_n + cand;
@@ -222,16 +250,17 @@ __global__ void __launch_bounds__(kEvalThreads, (CPT == 4 && NCB <= 8) ? 4 : 1) 
 }
 
 // ---- bucket dispatch: NXB in {2,4,8}; MODE 0 column buckets {2,5,8,11,17,28,72}; MODE 1 {3,10,28,55} ----
-template <int KERN, int NXB, int NCB, int CPT, int MODE>
+template <int KERN, int NXB, int NCB, int CPT, int RG, int MODE>
 static int launch_one(cudaStream_t s, int nitems, int ncols, const GpView* gps, const Item* items, const double* X,
                       int ldx, int chunk_n, int nrhs, double* panels, const double* beta, const RawOut* raws,
                       int ldraw) {
+    constexpr int threads = RG * (kBlk / CPT);
     if (MODE == 0 && nrhs == 1 && NCB <= 17)
-        eval_kernel<KERN, NXB, NCB, CPT, MODE, true><<<nitems, kEvalThreads, 0, s>>>(gps, items, X, ldx, chunk_n, nrhs, ncols,
-                                                                                     panels, beta, raws, ldraw);
+        eval_kernel<KERN, NXB, NCB, CPT, RG, MODE, true><<<nitems, threads, 0, s>>>(gps, items, X, ldx, chunk_n, nrhs, ncols,
+                                                                                    panels, beta, raws, ldraw);
     else
-        eval_kernel<KERN, NXB, NCB, CPT, MODE, false><<<nitems, kEvalThreads, 0, s>>>(gps, items, X, ldx, chunk_n, nrhs, ncols,
-                                                                                      panels, beta, raws, ldraw);
+        eval_kernel<KERN, NXB, NCB, CPT, RG, MODE, false><<<nitems, threads, 0, s>>>(gps, items, X, ldx, chunk_n, nrhs, ncols,
+                                                                                     panels, beta, raws, ldraw);
     GPD_CUDA(cudaGetLastError());
     return 0;
 }
@@ -240,12 +269,18 @@ template <int KERN, int NXB>
 static int dispatch_cols(cudaStream_t s, int mode, int nitems, int ncols, const GpView* gps, const Item* items,
                          const double* X, int ldx, int chunk_n, int nrhs, double* panels, const double* beta,
                          const RawOut* raws, int ldraw) {
+#ifndef GPD_EVAL_CPT_SMALL
+#define GPD_EVAL_CPT_SMALL 4
+#define GPD_EVAL_RG_SMALL 4
+#endif
 #define GPD_GO(NCB, CPT, MODE) \
-    return launch_one<KERN, NXB, NCB, CPT, MODE>(s, nitems, ncols, gps, items, X, ldx, chunk_n, nrhs, panels, beta, raws, ldraw)
+    return launch_one<KERN, NXB, NCB, CPT, CPT, MODE>(s, nitems, ncols, gps, items, X, ldx, chunk_n, nrhs, panels, beta, raws, ldraw)
+#define GPD_GO_SMALL(NCB, MODE) \
+    return launch_one<KERN, NXB, NCB, GPD_EVAL_CPT_SMALL, GPD_EVAL_RG_SMALL, MODE>(s, nitems, ncols, gps, items, X, ldx, chunk_n, nrhs, panels, beta, raws, ldraw)
     if (mode == 0) {
-        if (ncols <= 2) GPD_GO(2, 4, 0);
-        if (ncols <= 5) GPD_GO(5, 4, 0);
-        if (ncols <= 8) GPD_GO(8, 4, 0);
+        if (ncols <= 2) GPD_GO_SMALL(2, 0);
+        if (ncols <= 5) GPD_GO_SMALL(5, 0);
+        if (ncols <= 8) GPD_GO_SMALL(8, 0);
         if (ncols <= 11) GPD_GO(11, 4, 0);
         if (ncols <= 17) GPD_GO(17, 2, 0);
         if (ncols <= 28) GPD_GO(28, 2, 0);
@@ -260,6 +295,7 @@ static int dispatch_cols(cudaStream_t s, int mode, int nitems, int ncols, const 
     set_error("second variance derivative supports P <= 10 model parameters");
     return 3;
 #undef GPD_GO
+#undef GPD_GO_SMALL
 }
 
 template <int KERN>

@@ -314,8 +314,17 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) tri_kernel(const TriArgs args
                     for (int cc = 0; cc < kCps; ++cc) {
                         const double* sA = sm.A[stage] + cc * kChunkElems;
                         const double* sB = sm.B[stage] + cc * kChunkElems;
-                        if (diag) compute_chunk<WM, WN, true, BWD>(sA, sB, lane, wm, wn, c + cc, acc);
-                        else compute_chunk<WM, WN, false, BWD>(sA, sB, lane, wm, wn, c + cc, acc);
+                        // this warp's rows against this chunk's k range: dense, all zero, or straddling the diagonal
+                        int mode = 1;
+                        if (diag) {
+                            const int rlo = GPD_BLK(wm, 0, WM, MB) * 8, rhi = GPD_BLK(wm, MB - 1, WM, MB) * 8 + 7;
+                            const int klo = (c + cc) * kChunkK, khi = klo + kChunkK - 1;
+                            if (BWD ? (khi < rlo) : (klo > rhi)) mode = 0;
+                            else if (BWD ? (klo >= rhi) : (khi <= rlo)) mode = 1;
+                            else mode = 2;
+                        }
+                        if (mode == 1) compute_chunk<WM, WN, false, BWD>(sA, sB, lane, wm, wn, c + cc, acc);
+                        else if (mode == 2) compute_chunk<WM, WN, true, BWD>(sA, sB, lane, wm, wn, c + cc, acc);
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stage]));
