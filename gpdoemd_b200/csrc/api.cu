@@ -180,6 +180,7 @@ struct Plan {
     int flags = 0;
     bool transformed = false;       // X, outputs in the reference's transformed units (the `_`-hooks)
     bool need_W = false;            // variance derivatives: 1+P right-hand sides, V panels kept
+    bool skip_finalize = false;     // the fused scoring path converts units inside post1_kernel
     int chunk = 0, tiles = 0;
     std::vector<GpEntry> entries;
     std::vector<Group> groups;
@@ -470,7 +471,7 @@ static int run_chunk(gpd_ctx* c, Plan& pl, const double* X_dev, int ldx, int nc)
             }
         }
     }
-    for (int m = 0; m < M; ++m) {
+    for (int m = 0; m < M && !pl.skip_finalize; ++m) {
         gpd_model* mo = pl.models[m];
         ModelBufs& b = pl.mb[m];
         Span sp(c, F_MARG, 1, 0);
@@ -1237,7 +1238,10 @@ static int score_impl(gpd_ctx* c, gpd_model* const* models, int32_t M, const dou
         maxP = std::max(maxP, models[m]->P);
     }
     Plan pl;
-    size_t extra = sizeof(double) * ((size_t)M * E + (size_t)M * E * E + nk) + sizeof(double) * criterion_work_doubles(1, M, E);
+    pl.skip_finalize = (order == 1);
+    const bool keep_dc = dc_out != nullptr;
+    size_t extra = sizeof(double) * ((size_t)M * E + (size_t)M * E * E + nk) + sizeof(double) * criterion_work_doubles(1, M, E) +
+                   (crit_partial_bytes(kBlk, nk) + kBlk - 1) / kBlk;
     if (!x_on_device) extra += sizeof(double) * D;
     if (order == 2) extra += sizeof(double) * ((size_t)E * maxP * maxP + E);
     GPD_TRY(plan_build(c, models, M, order_flags(order), N, extra, 0, pl));
@@ -1247,22 +1251,32 @@ static int score_impl(gpd_ctx* c, gpd_model* const* models, int32_t M, const dou
     Bump bump(c->scratch.p, c->scratch.cap);
     const int Nc = pl.chunk;
     double* X_stage = x_on_device ? nullptr : bump.take<double>((size_t)Nc * D);
-    double* mu_all = bump.take<double>((size_t)Nc * M * E);
-    double* S_all = bump.take<double>((size_t)Nc * M * E * E);
-    double* dc_dev = bump.take<double>((size_t)Nc * nk);
+    double* mu_all = order == 2 ? bump.take<double>((size_t)Nc * M * E) : nullptr;
+    double* S_all = order == 2 ? bump.take<double>((size_t)Nc * M * E * E) : nullptr;
+    double* dc_dev = (keep_dc && !dc_on_device) ? bump.take<double>((size_t)Nc * nk) : nullptr;
     double* work = bump.take<double>(criterion_work_doubles(Nc, M, E));
     double* tmpA = order == 2 ? bump.take<double>((size_t)Nc * E * maxP * maxP) : nullptr;
     double* tmp_s2 = order == 2 ? bump.take<double>((size_t)Nc * E) : nullptr;
     double* d_noise = bump.take<double>((size_t)E * E);
     double* d_pps = bump.take<double>(M);
+    void* partial = bump.take<char>(crit_partial_bytes(Nc, nk));
+    PostModel* pms_dev = bump.take<PostModel>(M);
     GPD_TRY(plan_materialize(c, pl, bump));
-    for (int m = 0; m < M; ++m) {   // finalize writes the means straight into the (N, M, E) criterion layout
-        pl.mb[m].mu = mu_all + (size_t)m * E;
-        pl.mb[m].ldmu = M * E;
-    }
     cudaStream_t s = c->stream;
+    if (order == 2) {
+        for (int m = 0; m < M; ++m) {   // finalize writes the means straight into the (N, M, E) criterion layout
+            pl.mb[m].mu = mu_all + (size_t)m * E;
+            pl.mb[m].ldmu = M * E;
+        }
+    } else {
+        std::vector<PostModel> pms(M);
+        for (int m = 0; m < M; ++m) pms[m] = PostModel{models[m]->xf_dev, models[m]->P, pl.mb[m].ldraw, pl.mb[m].ng};
+        GPD_CUDA(cudaMemcpyAsync(pms_dev, pms.data(), sizeof(PostModel) * M, cudaMemcpyHostToDevice, s));
+    }
     GPD_CUDA(cudaMemcpyAsync(d_noise, noise, sizeof(double) * E * E, cudaMemcpyHostToDevice, s));
     GPD_CUDA(cudaMemcpyAsync(d_pps, pps, sizeof(double) * M, cudaMemcpyHostToDevice, s));
+    int kinds_h[kMaxKinds];
+    for (int k = 0; k < nk; ++k) kinds_h[k] = kinds[k];
     for (int64_t start = 0; start < N; start += Nc) {
         const int nc = (int)std::min<int64_t>(Nc, N - start);
         const double* Xc;
@@ -1273,29 +1287,32 @@ static int score_impl(gpd_ctx* c, gpd_model* const* models, int32_t M, const dou
             Xc = X_stage;
         }
         GPD_TRY(run_chunk(c, pl, Xc, D, nc));
-        for (int m = 0; m < M; ++m) {
-            gpd_model* mo = models[m];
-            const ModelBufs& b = pl.mb[m];
-            const double* Sigma_dev = (const double*)((const char*)mo->xf_dev + offsetof(ModelXform, Sigma));
-            Span sp(c, F_MARG, order == 2 ? 2 : 1, 0);
-            GPD_TRY(launch_assemble(s, order, nc, E, mo->P, b.mu, b.ldmu, b.s2, b.dmu, b.d2mu, b.d2s2, Sigma_dev,
-                                    S_all + (size_t)m * E * E, M * E * E, tmpA, tmp_s2));
-        }
-        for (int k = 0; k < nk; ++k) {
-            double* dc_target = (dc_out && dc_on_device) ? dc_out + (size_t)k * N + start : dc_dev + (size_t)k * Nc;
-            {
-                Span sp(c, F_CRIT, 2, 0);
-                GPD_TRY(launch_criterion(s, kinds[k], mu_all, S_all, nc, M, E, d_noise, d_pps, dc_target, work));
+        if (order == 1) {
+            Span sp(c, F_MARG, 1, 0);
+            GPD_TRY(launch_post1(s, pms_dev, pl.raws_dev, M, E, nc, nc, d_noise, work, kinds_h, nk));
+        } else {
+            for (int m = 0; m < M; ++m) {
+                gpd_model* mo = models[m];
+                const ModelBufs& b = pl.mb[m];
+                const double* Sigma_dev = (const double*)((const char*)mo->xf_dev + offsetof(ModelXform, Sigma));
+                Span sp(c, F_MARG, 2, 0);
+                GPD_TRY(launch_assemble(s, order, nc, E, mo->P, b.mu, b.ldmu, b.s2, b.dmu, b.d2mu, b.d2s2, Sigma_dev,
+                                        S_all + (size_t)m * E * E, M * E * E, tmpA, tmp_s2));
             }
-            {
-                Span sp(c, F_ARGMAX, 2, 0);
-                GPD_TRY(launch_argmax(s, dc_target, nc, idx_offset + start, c->best_val_dev + k, c->best_idx_dev + k,
-                                      start == 0, c->argmax_partial));
-            }
-            if (dc_out && !dc_on_device)
-                GPD_CUDA(cudaMemcpyAsync(dc_out + (size_t)k * N + start, dc_target, sizeof(double) * nc,
-                                         cudaMemcpyDeviceToHost, s));
+            Span sp(c, F_CRIT, 1, 0);
+            GPD_TRY(launch_crit_prep(s, mu_all, S_all, nc, M, E, d_noise, work, kinds_h, nk));
         }
+        double* dcp[kMaxKinds];
+        for (int k = 0; k < nk; ++k)
+            dcp[k] = !keep_dc ? nullptr : (dc_on_device ? dc_out + (size_t)k * N + start : dc_dev + (size_t)k * Nc);
+        {
+            Span sp(c, F_CRIT, 2, 0);
+            GPD_TRY(launch_crit_multi(s, kinds_h, nk, dcp, nc, M, E, d_noise, d_pps, work, idx_offset + start, partial,
+                                      start == 0, c->best_val_dev, c->best_idx_dev));
+        }
+        if (keep_dc && !dc_on_device)
+            for (int k = 0; k < nk; ++k)
+                GPD_CUDA(cudaMemcpyAsync(dc_out + (size_t)k * N + start, dcp[k], sizeof(double) * nc, cudaMemcpyDeviceToHost, s));
     }
     long long bi[kMaxKinds];
     double bv[kMaxKinds];

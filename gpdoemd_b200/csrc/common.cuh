@@ -56,6 +56,11 @@ struct ModelXform {              // device copy of the per-model unit conversion
     double Sigma[kMaxP * kMaxP]; // row-major, stride P
 };
 
+struct PostModel {               // per model slot of a fused scoring call (device table)
+    const ModelXform* xf;
+    int P, ldraw, npart;
+};
+
 void set_error(const std::string& msg);
 #define GPD_CUDA(call)                                                                        \
     do {                                                                                      \
@@ -116,6 +121,14 @@ size_t criterion_work_doubles(int N, int M, int E);
 int launch_argmax(cudaStream_t s, const double* dc, long long N, long long idx_base, double* best_val_dev,
                   long long* best_idx_dev, int first, void* partial_dev);
 size_t argmax_partial_bytes();
+size_t crit_partial_bytes(int N, int nk);
+int launch_post1(cudaStream_t s, const PostModel* pms_dev, const RawOut* raws_dev, int M, int E, int N, int chunk_n,
+                 const double* noise_dev, double* work, const int* kinds, int nk);
+int launch_crit_prep(cudaStream_t s, const double* mu, const double* S, int N, int M, int E, const double* noise_dev,
+                     double* work, const int* kinds, int nk);
+int launch_crit_multi(cudaStream_t s, const int* kinds, int nk, double* const* dc, int N, int M, int E,
+                      const double* noise_dev, const double* pps_dev, double* work, long long idx_base, void* partial_dev,
+                      int first, double* best_val_dev, long long* best_idx_dev);
 int launch_fill_uniform(cudaStream_t s, double* X, long long N, int D, uint64_t seed, long long first_row,
                         const double* lo_dev, const double* hi_dev);
 int launch_flush(cudaStream_t s, double* buf, size_t n);

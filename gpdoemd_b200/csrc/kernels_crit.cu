@@ -268,10 +268,8 @@ __global__ void __launch_bounds__(128) crit_prep_kernel(const double* __restrict
 #define MUS(m, a) w.mu[((size_t)(m) * E + (a)) * N + n]
 
 template <int E>
-__global__ void __launch_bounds__(128) crit_kernel(int kind, int N, int M, const double* __restrict__ noise,
-                                                   const double* __restrict__ pps, CritWork w, double* __restrict__ dc) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+__device__ __forceinline__ double crit_eval(int kind, int n, int N, int M, const double* __restrict__ noise,
+                                            const double* __restrict__ pps, const CritWork& w) {
     double out = 0.0;
     if (kind == 0) {                                   // HR  design_criteria.py:49-63
         for (int i = 0; i < M - 1; ++i)
@@ -396,7 +394,15 @@ __global__ void __launch_bounds__(128) crit_kernel(int kind, int N, int M, const
         }
         out = ((0.5 * E) * log2pi - log(T2)) - T1;
     }
-    dc[n] = out;
+    return out;
+}
+
+template <int E>
+__global__ void __launch_bounds__(128) crit_kernel(int kind, int N, int M, const double* __restrict__ noise,
+                                                   const double* __restrict__ pps, CritWork w, double* __restrict__ dc) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    dc[n] = crit_eval<E>(kind, n, N, M, noise, pps, w);
 }
 #undef SOA
 #undef MUS
@@ -505,7 +511,195 @@ __global__ void __launch_bounds__(256) argmax_stage2(const Best* __restrict__ pa
     }
 }
 
-size_t argmax_partial_bytes() { return sizeof(Best) * kArgmaxBlocks; }
+size_t argmax_partial_bytes() { return sizeof(Best) * kArgmaxBlocks * kMaxKinds; }
+
+// ---------------------------------------------------------------------------------------------
+// Fused first-order post-processing of the scoring path (one launch each):
+//   post1_kernel      raw contractions -> units -> S = diag(s2) + J Sigma J^T (clipped) -> + noise -> inverse, det
+//                     written straight into the criterion workspace (SoA); replaces M finalize + M assemble +
+//                     crit_prep launches.  Same arithmetic order as finalize_kernel / assemble_kernel.
+//   crit_multi_kernel every requested criterion for a candidate in one thread + per-block (max, index)
+//   argmax_final      one block per criterion folds the block partials into the running best
+// ---------------------------------------------------------------------------------------------
+template <int E>
+__global__ void __launch_bounds__(128) post1_kernel(const PostModel* __restrict__ pms, const RawOut* __restrict__ raws,
+                                                    int M, int N, int chunk_n, const double* __restrict__ noise,
+                                                    CritWork w, int need_inv) {
+    long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (long long)N * M) return;
+    const int m = (int)(tid / N), n = (int)(tid % N);
+    const PostModel pm = pms[m];
+    const ModelXform* __restrict__ xf = pm.xf;
+    const RawOut& raw = raws[m];
+    const int P = pm.P;
+    double J[E][kMaxP], s2[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const size_t row = (size_t)e * chunk_n + n;
+        const double* c = raw.cmu + row * pm.ldraw;
+        const double ystd = xf->ystd[e];
+        const double* gr = raw.gram + row * pm.npart;
+        double vv = gr[0];
+        for (int k = 1; k < pm.npart; ++k) vv += gr[k];
+        w.mu[((size_t)m * E + e) * N + n] = xf->ymean[e] + c[0] * ystd;
+        s2[e] = (raw.kss[row] - vv) * (ystd * ystd);
+        for (int a = 0; a < P; ++a) J[e][a] = c[1 + a] * ystd / xf->pdiff[a];
+    }
+    double A[E][E];
+#pragma unroll
+    for (int e1 = 0; e1 < E; ++e1)
+#pragma unroll
+        for (int e2 = 0; e2 < E; ++e2) {
+            double v = 0.0;
+            for (int a = 0; a < P; ++a) {
+                double t = 0.0;
+                for (int b = 0; b < P; ++b) t = fma(xf->Sigma[a * P + b], J[e2][b], t);
+                v = fma(J[e1][a], t, v);
+            }
+            if (e1 == e2) v = fmax(1e-15, s2[e1] + v);
+            A[e1][e2] = v + noise[e1 * E + e2];
+            w.Sn[((size_t)(m * E + e1) * E + e2) * N + n] = A[e1][e2];
+        }
+    if (!need_inv) return;
+    const double det = inv_inplace<E>(A);
+    w.dS[(size_t)m * N + n] = det;
+#pragma unroll
+    for (int a = 0; a < E; ++a)
+#pragma unroll
+        for (int b = 0; b < E; ++b) w.iS[((size_t)(m * E + a) * E + b) * N + n] = A[a][b];
+}
+
+struct KindList { int n; int kind[kMaxKinds]; double* dc[kMaxKinds]; };
+
+template <int E>
+__global__ void __launch_bounds__(128) crit_multi_kernel(KindList kl, int N, int M, const double* __restrict__ noise,
+                                                         const double* __restrict__ pps, CritWork w, long long idx_base,
+                                                         Best* __restrict__ partial) {
+    __shared__ Best sh[8];
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int k = 0; k < kl.n; ++k) {
+        Best x{0.0, -1};
+        if (n < N) {
+            const double v = crit_eval<E>(kl.kind[k], n, N, M, noise, pps, w);
+            if (kl.dc[k]) kl.dc[k][n] = v;
+            x.v = v;
+            x.i = idx_base + n;
+        }
+        x = block_best(x, sh);
+        if (threadIdx.x == 0) partial[(size_t)k * gridDim.x + blockIdx.x] = x;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) argmax_final(const Best* __restrict__ partial, int nparts, int first,
+                                                    double* __restrict__ best_val, long long* __restrict__ best_idx) {
+    __shared__ Best sh[8];
+    const int k = blockIdx.x;
+    Best x{0.0, -1};
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
+        Best p = partial[(size_t)k * nparts + i];
+        if (p.i >= 0 && (x.i < 0 || better(p.v, p.i, x.v, x.i))) x = p;
+    }
+    x = block_best(x, sh);
+    if (threadIdx.x == 0) {
+        if (!first) {
+            Best cur{best_val[k], best_idx[k]};
+            if (cur.i >= 0 && (x.i < 0 || better(cur.v, cur.i, x.v, x.i))) x = cur;
+        }
+        best_val[k] = x.v;
+        best_idx[k] = x.i;
+    }
+}
+
+size_t crit_partial_bytes(int N, int nk) { return sizeof(Best) * (size_t)((N + 127) / 128) * nk; }
+
+static CritWork make_work(double* work, int N, int M, int E) {
+    CritWork w;
+    w.Sn = work;
+    w.iS = w.Sn + (size_t)N * M * E * E;
+    w.dS = w.iS + (size_t)N * M * E * E;
+    w.mu = w.dS + (size_t)N * M;
+    return w;
+}
+
+template <int E>
+static int post1_dispatch(cudaStream_t s, const PostModel* pms, const RawOut* raws, int M, int N, int chunk_n,
+                          const double* noise, double* work, int need_inv) {
+    long long total = (long long)N * M;
+    post1_kernel<E><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(pms, raws, M, N, chunk_n, noise,
+                                                                    make_work(work, N, M, E), need_inv);
+    GPD_CUDA(cudaGetLastError());
+    return 0;
+}
+template <int E>
+static int crit_multi_dispatch(cudaStream_t s, const KindList& kl, int N, int M, const double* noise, const double* pps,
+                               double* work, long long idx_base, void* partial) {
+    crit_multi_kernel<E><<<(N + 127) / 128, 128, 0, s>>>(kl, N, M, noise, pps, make_work(work, N, M, E), idx_base,
+                                                         (Best*)partial);
+    GPD_CUDA(cudaGetLastError());
+    return 0;
+}
+template <int E>
+static int crit_prep_dispatch(cudaStream_t s, const double* mu, const double* S, int N, int M, const double* noise,
+                              double* work, int need_inv) {
+    long long total = (long long)N * M;
+    crit_prep_kernel<E><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(mu, S, N, M, noise, make_work(work, N, M, E), need_inv);
+    GPD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+#define GPD_E_SWITCH(FN, ...)                                   \
+    switch (E) {                                                \
+        case 1: return FN<1>(__VA_ARGS__);                      \
+        case 2: return FN<2>(__VA_ARGS__);                      \
+        case 3: return FN<3>(__VA_ARGS__);                      \
+        case 4: return FN<4>(__VA_ARGS__);                      \
+        case 5: return FN<5>(__VA_ARGS__);                      \
+        case 6: return FN<6>(__VA_ARGS__);                      \
+        case 7: return FN<7>(__VA_ARGS__);                      \
+        case 8: return FN<8>(__VA_ARGS__);                      \
+        default:                                                \
+            set_error("criteria support 1 <= E <= 8 outputs"); \
+            return 3;                                           \
+    }
+
+static int need_inverse(const int* kinds, int nk) {
+    for (int k = 0; k < nk; ++k)
+        if (kinds[k] == 1 || kinds[k] == 3 || kinds[k] == 4) return 1;
+    return 0;
+}
+
+int launch_post1(cudaStream_t s, const PostModel* pms_dev, const RawOut* raws_dev, int M, int E, int N, int chunk_n,
+                 const double* noise_dev, double* work, const int* kinds, int nk) {
+    const int inv = need_inverse(kinds, nk);
+    GPD_E_SWITCH(post1_dispatch, s, pms_dev, raws_dev, M, N, chunk_n, noise_dev, work, inv)
+}
+
+int launch_crit_prep(cudaStream_t s, const double* mu, const double* S, int N, int M, int E, const double* noise_dev,
+                     double* work, const int* kinds, int nk) {
+    const int inv = need_inverse(kinds, nk);
+    GPD_E_SWITCH(crit_prep_dispatch, s, mu, S, N, M, noise_dev, work, inv)
+}
+
+int launch_crit_multi(cudaStream_t s, const int* kinds, int nk, double* const* dc, int N, int M, int E,
+                      const double* noise_dev, const double* pps_dev, double* work, long long idx_base, void* partial_dev,
+                      int first, double* best_val_dev, long long* best_idx_dev) {
+    KindList kl;
+    kl.n = nk;
+    for (int k = 0; k < nk; ++k) {
+        kl.kind[k] = kinds[k];
+        kl.dc[k] = dc ? dc[k] : nullptr;
+    }
+    {
+        auto go = [&]() -> int { GPD_E_SWITCH(crit_multi_dispatch, s, kl, N, M, noise_dev, pps_dev, work, idx_base, partial_dev) };
+        GPD_TRY(go());
+    }
+    argmax_final<<<nk, 256, 0, s>>>((const Best*)partial_dev, (N + 127) / 128, first, best_val_dev, best_idx_dev);
+    GPD_CUDA(cudaGetLastError());
+    return 0;
+}
+#undef GPD_E_SWITCH
+
 
 int launch_argmax(cudaStream_t s, const double* dc, long long N, long long idx_base, double* best_val_dev,
                   long long* best_idx_dev, int first, void* partial_dev) {
