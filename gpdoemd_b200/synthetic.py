@@ -55,8 +55,9 @@ def build_models(cls, seed, M, E, D, P, n, kernel, n_binary=0, kernel_lookup=Non
     """Instantiate ``cls`` (gpdoemd_b200.GPModel or an API-compatible class) for M rival models."""
     models, datas = [], []
     for m in range(M):
-        d = model_data(seed * 1000 + m, E, D, P, n, n_binary, gp_noise, kernel)
-        mo = cls({'name': 'm%d' % m, 'call': (lambda x, p: None), 'dim_x': D, 'dim_p': P, 'num_outputs': E,
+        Pm = P[m] if isinstance(P, (list, tuple)) else P          # rival models may differ in dim_p
+        d = model_data(seed * 1000 + m, E, D, Pm, n, n_binary, gp_noise, kernel)
+        mo = cls({'name': 'm%d' % m, 'call': (lambda x, p: None), 'dim_x': D, 'dim_p': Pm, 'num_outputs': E,
                   'meas_noise_var': 0.01, 'binary_variables': d['binary']}, **kw)
         k = kernel if kernel_lookup is None else kernel_lookup[kernel]
         mo.gp_surrogate(Z=d['Z'], Y=d['Y'], kern_x=k, kern_p=k)

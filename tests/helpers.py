@@ -17,6 +17,12 @@ def gpu_models(oracle_ms):
     return [GPModel.from_reference(m) for m in oracle_ms]
 
 
+def demo_mesh(xlo, xhi, num=20):
+    """demos/case_study.py:203-207: 20 x 20 x {0, 1} mesh, third design variable binary."""
+    g = np.meshgrid(np.linspace(xlo[0], xhi[0], num), np.linspace(xlo[1], xhi[1], num), [0, 1])
+    return np.vstack([np.ravel(a) for a in g]).T
+
+
 def relerr(a, b, scale=None):
     """max |a-b| / max(|b|, scale): relative error with a floor at the quantity's natural scale."""
     a, b = np.asarray(a), np.asarray(b)

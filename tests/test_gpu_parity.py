@@ -230,6 +230,33 @@ def test_fused_score_matches_stepwise_oracle(order, crit, gpu_ctx):
     assert np.array_equal(d2, d1) and bi2 == bi + 1000 and bv2 == bv
 
 
+@pytest.mark.parametrize('P', [1, [1, 2, 3, 2, 4]])
+def test_c1_demo_shapes(P, gpu_ctx):
+    """BASELINE config 1 shapes (demos/case_study.py:134-307, mixing case study): M=5 rival models, E=1,
+    D=3 with the third design variable binary, 1600 training rows split over the two binary values, the
+    20 x 20 x 2 candidate mesh, Matern52, Taylor first order, all criteria; also rival models of different dim_p."""
+    import gpdoemd_b200 as g
+    oms, ds = helpers.oracle_models(51, M=5, E=1, D=3, P=P, n=1600, kernel='Matern52', n_binary=1)
+    gms = helpers.gpu_models(oms)
+    lo = np.max([d['xlo'] for d in ds], axis=0)
+    hi = np.min([d['xhi'] for d in ds], axis=0)
+    X = helpers.demo_mesh(lo, hi)
+    assert X.shape == (800, 3)
+    mu = np.zeros((800, 5, 1))
+    S = np.zeros((800, 5, 1, 1))
+    for i, om in enumerate(oms):
+        mu[:, i], S[:, i] = omarg.taylor_first_order(om, X)
+        Mg, Sg = g.taylor_first_order(gms[i], X)
+        assert helpers.relerr(Mg, mu[:, i], om.ystd) < TOL_MEAN
+        assert helpers.relerr(Sg, S[:, i], S[:, i].max()) < TOL_VAR
+    measvar = np.array([0.05]) ** 2
+    res = g.score_designs_multi(gms, X, ['HR', 'BH', 'BF', 'AW', 'JR'], order=1, noise_var=measvar)
+    for name in ('HR', 'BH', 'BF', 'AW', 'JR'):
+        d0 = ocrit.CRITERIA[name](mu, S, measvar, None)
+        assert helpers.relerr(res[name][2], d0, np.abs(d0).mean()) < TOL_CRIT, name
+        assert res[name][0] == int(np.argmax(d0)), name
+
+
 def test_full_size_properties_c2(gpu_ctx):
     """BASELINE config 2 at full size (N=1e5, n=500, M=4, E=2, RBF): size-independent properties."""
     import gpdoemd_b200 as g
