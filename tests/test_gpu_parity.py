@@ -288,3 +288,65 @@ def test_full_size_properties_c2(gpu_ctx):
     ytrue = m0.trans_y(m0.Y[:1], back=True)
     assert np.allclose(Mtr, ytrue, atol=1e-3 * m0.ystd.max())
     assert np.all(Str < 1e-4 * m0.ystd ** 2)
+
+
+def test_accuracy_vs_extended_precision(gpu_ctx):
+    """80-bit truth for mean, variance and their first p-derivatives on an RBF GP (the worst conditioned
+    kernel): the CUDA path is at least as close to the truth as the float64 oracle (GPy's algorithm, which
+    forms K^-1 explicitly for the variance derivative), and well inside the stated tolerances."""
+    oms, ds = helpers.oracle_models(61, M=1, E=1, D=2, P=2, n=120, kernel='RBF')
+    om = oms[0]
+    gm = helpers.gpu_models(oms)[0]
+    from gpdoemd_b200 import synthetic
+    X = synthetic.candidates(2, 40, 2, ds[0]['xlo'], ds[0]['xhi'])
+    gp = om.gps[0][0]
+    ld = np.longdouble
+    n = len(gp.X)
+    pstar = om.trans_p(om.pmean)
+    Z = np.c_[om.trans_x(X), np.tile(pstar, (len(X), 1))].astype(ld)
+    Xt = gp.X.astype(ld)
+    kx, kp = gp.kern.kernx, gp.kern.kernp
+
+    def part(k, A, B):
+        a = A[:, k.active_dims] / k.lengthscale.astype(ld)
+        b = B[:, k.active_dims] / k.lengthscale.astype(ld)
+        return ld(k.variance) * np.exp(-((a[:, None, :] - b[None, :, :]) ** 2).sum(-1) / 2)
+    Ky = part(kx, Xt, Xt) * part(kp, Xt, Xt) + np.eye(n, dtype=ld) * ld(gp.noise_var + 1e-8)
+    L = np.zeros((n, n), dtype=ld)
+    for j in range(n):
+        L[j, j] = np.sqrt(Ky[j, j] - (L[j, :j] ** 2).sum())
+        L[j + 1:, j] = (Ky[j + 1:, j] - L[j + 1:, :j].dot(L[j, :j])) / L[j, j]
+
+    def fsub(B):
+        Y = np.zeros_like(B)
+        for i in range(n):
+            Y[i] = (B[i] - L[i, :i].dot(Y[:i])) / L[i, i]
+        return Y
+    w = fsub(gp.Y.astype(ld))                      # L^-1 y
+    Ks = part(kx, Xt, Z) * part(kp, Xt, Z)         # (n, N)
+    V = fsub(Ks)
+    mu_t = (V * w).sum(0)
+    kss = ld(kx.variance * kp.variance)
+    var_t = kss - (V ** 2).sum(0)
+    # d k_i / d p_a = k_i * (P_ia - p*_a) / l_a^2   (RBF)
+    dmu_t = np.zeros((len(X), 2), dtype=ld)
+    dvar_t = np.zeros((len(X), 2), dtype=ld)
+    for a in range(2):
+        col = kp.active_dims[a]
+        dK = Ks * ((Xt[:, col][:, None] - Z[:, col][None, :]) / ld(kp.lengthscale[a]) ** 2)
+        W = fsub(dK)
+        dmu_t[:, a] = (W * w).sum(0)
+        dvar_t[:, a] = -2 * (W * V).sum(0)
+    ystd, pd = ld(om.ystd[0]), (om.pmax - om.pmin).astype(ld)
+    truth = {'mu': om.ymean[0] + mu_t * ystd, 's2': var_t * ystd ** 2, 'dmu': dmu_t * ystd / pd, 'ds2': dvar_t * ystd ** 2 / pd}
+    scale = {'mu': float(ystd), 's2': float(kss * ystd ** 2), 'dmu': float(ystd / pd.min()),
+             'ds2': float(kss * ystd ** 2 / pd.min())}
+    got_o = {'mu': om.predict(X)[0][:, 0], 's2': om.predict(X)[1][:, 0], 'dmu': om.d_mu_d_p(0, X), 'ds2': om.d_s2_d_p(0, X)}
+    got_g = {'mu': gm.predict(X)[0][:, 0], 's2': gm.predict(X)[1][:, 0], 'dmu': gm.d_mu_d_p(0, X), 'ds2': gm.d_s2_d_p(0, X)}
+    for k in truth:
+        t = np.asarray(truth[k], dtype=float)
+        eo = np.max(np.abs(got_o[k] - t)) / scale[k]
+        eg = np.max(np.abs(got_g[k] - t)) / scale[k]
+        print('%-4s error vs 80-bit truth / scale: oracle %.2e  cuda %.2e' % (k, eo, eg))
+        assert eg < 1e-9, (k, eg)
+        assert eg < max(3 * eo, 1e-12), (k, eg, eo)
