@@ -26,8 +26,9 @@ UNIT = 'designs/s'
 
 
 def workload_name(cfg, name):
-    return ('%s: synthetic M=%d models, E=%d outputs, D=%d, P=%d, n_train=%d %s GPs, N=%g candidates per GPU, '
-            'Taylor order %d + %s' % (name, cfg['M'], cfg['E'], cfg['D'], cfg['P'], cfg['n'], cfg['kernel'], cfg['N'],
+    kind = '%s GPs' % cfg['kernel'] if not cfg.get('inducing') else '%s sparse GPs (%d inducing inputs)' % (cfg['kernel'], cfg['inducing'])
+    return ('%s: synthetic M=%d models, E=%d outputs, D=%d, P=%d, n_train=%d %s, N=%g candidates per GPU, '
+            'Taylor order %d + %s' % (name, cfg['M'], cfg['E'], cfg['D'], cfg['P'], cfg['n'], kind, cfg['N'],
                                       cfg['order'], '/'.join(cfg['criteria'])))
 
 
@@ -35,7 +36,7 @@ def algorithmic_flops_per_candidate(cfg):
     """per GP n^2 (first order) or (P+2) n^2 (second order) for the triangular contraction,
     the dominant kernel; the evaluation/criteria terms are reported separately in DESIGN.md."""
     G = cfg['M'] * cfg['E']
-    n, P = cfg['n'], cfg['P']
+    n, P = cfg.get('inducing') or cfg['n'], cfg['P']
     return G * (n * n if cfg['order'] == 1 else (P + 2) * n * n)
 
 
@@ -82,9 +83,10 @@ def cpu_reference_run(cfg, seed, n_sample, steps, warmup):
     from oracle import criteria as ocrit
     from oracle import gpy_kernels
     from oracle import marginal as omarg
-    from oracle.model import OracleGPModel
-    oms, ds = synthetic.build_models(OracleGPModel, seed, cfg['M'], cfg['E'], cfg['D'], cfg['P'], cfg['n'],
-                                     cfg['kernel'], kernel_lookup=gpy_kernels.KERNELS)
+    from oracle.model import OracleGPModel, OracleSparseGPModel
+    sparse = dict(num_inducing=cfg['inducing'], gp_noise=1e-4) if cfg.get('inducing') else {}
+    oms, ds = synthetic.build_models(OracleSparseGPModel if sparse else OracleGPModel, seed, cfg['M'], cfg['E'], cfg['D'],
+                                     cfg['P'], cfg['n'], cfg['kernel'], kernel_lookup=gpy_kernels.KERNELS, **sparse)
     lo = np.max([d['xlo'] for d in ds], axis=0)
     hi = np.min([d['xhi'] for d in ds], axis=0)
     X = synthetic.candidates(7, n_sample, cfg['D'], lo, hi)
@@ -112,7 +114,7 @@ def cpu_reference_run(cfg, seed, n_sample, steps, warmup):
 
 def cpu_sample_size(cfg):
     # ~10-30 s of CPU work per run: the oracle does ~700 designs/s on C2 (8 cores) and far less on n=4000
-    per = {'C2': 4000, 'C3': 48, 'C4': 64, 'C5': 256}
+    per = {'C2': 4000, 'C3': 48, 'C4': 64, 'C5': 256, 'S2': 4000}
     return per
 
 
@@ -175,12 +177,13 @@ def main():
         ctx.set_option('tri_variant', args.tri_variant)
     if args.tri_cps is not None:
         ctx.set_option('tri_cps', args.tri_cps)
-    if cfg['n'] >= 2000:
+    if (cfg.get('inducing') or cfg['n']) >= 2000:
         ctx.set_scratch_bytes(64 << 30)
 
     # ---- problem: identical GP state on every rank, candidates = this rank's contiguous shard ----------
-    models, ds = synthetic.build_models(g.GPModel, seed, cfg['M'], cfg['E'], cfg['D'], cfg['P'], cfg['n'], cfg['kernel'],
-                                        device=local_rank)
+    sparse = dict(num_inducing=cfg['inducing'], gp_noise=1e-4) if cfg.get('inducing') else {}
+    models, ds = synthetic.build_models(g.SparseGPModel if sparse else g.GPModel, seed, cfg['M'], cfg['E'], cfg['D'],
+                                        cfg['P'], cfg['n'], cfg['kernel'], device=local_rank, **sparse)
     lo = np.max([d['xlo'] for d in ds], axis=0)
     hi = np.min([d['xhi'] for d in ds], axis=0)
     N, D = cfg['N'], cfg['D']

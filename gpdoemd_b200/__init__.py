@@ -8,11 +8,11 @@ or device is missing (there is no CPU fallback).
 from . import design_criteria, kernels, marginal, scoring, synthetic
 from .context import Context, get_context
 from .design_criteria import AW, BF, BH, HR, JR
-from .gp_state import ExactGP, GPState
+from .gp_state import ExactGP, GPState, SparseGP
 from .marginal import taylor_first_order, taylor_second_order
-from .models import GPModel
+from .models import GPModel, SparseGPModel
 from .scoring import ShardedScorer, score_designs, score_designs_dev, score_designs_multi
 
-__all__ = ['GPModel', 'GPState', 'ExactGP', 'Context', 'get_context', 'kernels', 'marginal', 'design_criteria',
+__all__ = ['GPModel', 'SparseGPModel', 'GPState', 'ExactGP', 'SparseGP', 'Context', 'get_context', 'kernels', 'marginal', 'design_criteria',
            'scoring', 'taylor_first_order', 'taylor_second_order', 'HR', 'BH', 'BF', 'AW', 'JR', 'score_designs',
            'score_designs_dev', 'score_designs_multi', 'ShardedScorer', 'synthetic']

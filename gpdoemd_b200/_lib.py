@@ -24,7 +24,7 @@ class GpDesc(C.Structure):
     _fields_ = [('kernel', C.c_int32), ('n', C.c_int32), ('dim_x', C.c_int32), ('dim_p', C.c_int32),
                 ('n_x_active', C.c_int32), ('x_active', c_int32_p), ('var_x', C.c_double), ('ls_x', c_double_p),
                 ('power_x', C.c_double), ('var_p', C.c_double), ('ls_p', c_double_p), ('power_p', C.c_double),
-                ('Z', c_double_p), ('alpha', c_double_p), ('L', c_double_p)]
+                ('Z', c_double_p), ('alpha', c_double_p), ('L', c_double_p), ('factor_kind', C.c_int32)]
 
 
 class GpdError(RuntimeError):

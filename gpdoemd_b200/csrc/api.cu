@@ -740,6 +740,7 @@ int gpd_gp_upload(gpd_ctx* c, const gpd_gp_desc* d, gpd_gp** out) {
     GPD_CHECK(c && d && out, "null argument");
     *out = nullptr;
     GPD_CHECK(d->kernel >= 0 && d->kernel <= 5, "unknown kernel id");
+    GPD_CHECK(d->factor_kind == GPD_FACTOR_CHOL || d->factor_kind == GPD_FACTOR_ROOT, "unknown factor_kind");
     GPD_CHECK(d->n >= 1, "empty training set");
     GPD_CHECK(d->dim_p >= 1 && d->dim_p <= kMaxP, "dim_p out of range (1..16)");
     GPD_CHECK(d->n_x_active >= 1 && d->n_x_active <= kMaxXDims, "x-kernel acts on 1..8 non-binary design dimensions");
@@ -814,7 +815,7 @@ int gpd_gp_upload(gpd_ctx* c, const gpd_gp_desc* d, gpd_gp** out) {
     cudaError_t e1 = cudaMemcpyAsync(L_dev, d->L, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, s);
     if (e1 == cudaSuccess) {
         uint64_t nl = 0;
-        rc = launch_invert_and_pack(s, L_dev, n, n_pad, dense, g->LinvF, g->LinvB, &nl);
+        rc = launch_invert_and_pack(s, L_dev, n, n_pad, dense, g->LinvF, g->LinvB, &nl, d->factor_kind);
         c->launches += nl;
         if (c->profile) c->fam_launches[F_SETUP] += nl;
     }

@@ -98,7 +98,7 @@ int launch_beta_contract(cudaStream_t s, const GpView* gps_dev, const Item* item
                          const double* beta_panels, const RawOut* raw_dev);
 // kernels_tri.cu
 int launch_invert_and_pack(cudaStream_t s, const double* L_dev, int n, int n_pad, double* dense_tmp,
-                           double* packF, double* packB, uint64_t* launches);
+                           double* packF, double* packB, uint64_t* launches, int factor_kind);
 int launch_tri(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int nitems, int nwork_rhs,
                int in_stride, int out_stride, int backward, const double* panels_in, double* panels_out,
                const RawOut* raw_dev, int ng, int chunk_n, int num_sms, int variant, int cps);

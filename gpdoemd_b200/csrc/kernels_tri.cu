@@ -584,17 +584,34 @@ __global__ void __launch_bounds__(256) pack_kernel(const double* __restrict__ X,
     }
 }
 
+// dense n_pad x n_pad copy of the lower triangle of an n x n operator, zero elsewhere
+__global__ void __launch_bounds__(256) copy_lower_kernel(const double* __restrict__ T, int n, int n_pad,
+                                                         double* __restrict__ X) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)n * n) return;
+    const int i = (int)(e / n), k = (int)(e % n);
+    if (k <= i) X[(size_t)i * n_pad + k] = T[e];
+}
+
 int launch_invert_and_pack(cudaStream_t s, const double* L_dev, int n, int n_pad, double* dense_tmp, double* packF,
-                           double* packB, uint64_t* launches) {
+                           double* packB, uint64_t* launches, int factor_kind) {
     const int nblk = n_pad / kBlk;
     GPD_CUDA(cudaMemsetAsync(dense_tmp, 0, sizeof(double) * (size_t)n_pad * n_pad, s));
-    diag_inv_kernel<<<nblk, kBlk, 0, s>>>(L_dev, n, n_pad, dense_tmp);
-    GPD_CUDA(cudaGetLastError());
-    *launches += 1;
-    for (int J = 1; J < nblk; ++J) {
-        offdiag_kernel<<<dim3(J, 4), 256, 0, s>>>(L_dev, n, n_pad, J, dense_tmp);
+    if (factor_kind == 1) {
+        // the operator is supplied directly (sparse GP: woodbury_inv = T^T T): nothing to invert
+        const long long total = (long long)n * n;
+        copy_lower_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(L_dev, n, n_pad, dense_tmp);
         GPD_CUDA(cudaGetLastError());
         *launches += 1;
+    } else {
+        diag_inv_kernel<<<nblk, kBlk, 0, s>>>(L_dev, n, n_pad, dense_tmp);
+        GPD_CUDA(cudaGetLastError());
+        *launches += 1;
+        for (int J = 1; J < nblk; ++J) {
+            offdiag_kernel<<<dim3(J, 4), 256, 0, s>>>(L_dev, n, n_pad, J, dense_tmp);
+            GPD_CUDA(cudaGetLastError());
+            *launches += 1;
+        }
     }
     const int ntiles = (int)packed_tiles(nblk);
     if (packF) {

@@ -87,11 +87,100 @@ class ExactGP:
         self.posterior = _Posterior(L, alpha)
 
 
+class SparseGP(ExactGP):
+    """Sparse GP regression with inducing inputs (what GPy's SparseGPRegression / VarDTC computes): the host
+    setup behind ``SparseGPModel`` (GPdoemd/models/sparse_gp_model.py:72).  ``gp[:]`` = inducing inputs
+    (row-major), kernel parameters, noise.  The posterior is (woodbury_vector, woodbury_inv) on the inducing
+    inputs, which are ``_predictive_variable`` exactly as the reference's hooks expect."""
+    is_sparse = True
+
+    def __init__(self, X, Y, kern, num_inducing=10, Z=None, rng=None, noise_var=1.0):
+        X = np.ascontiguousarray(X, dtype=float)
+        if Z is None:
+            rng = np.random.default_rng(0) if rng is None else rng
+            Z = X[rng.permutation(len(X))[:min(num_inducing, len(X))]].copy()
+        self.Z = np.ascontiguousarray(Z, dtype=float)
+        self.num_inducing = len(self.Z)
+        super().__init__(X, Y, kern, noise_var)
+
+    def __getitem__(self, key):
+        assert key == slice(None)
+        return np.r_[self.Z.ravel(), self.kern.get_params(), self.noise_var]
+
+    def __setitem__(self, key, v):
+        assert key == slice(None)
+        v = np.asarray(v, dtype=float)
+        nz = self.Z.size
+        self.Z = v[:nz].reshape(self.Z.shape).copy()
+        k = self.kern.set_params(v[nz:])
+        assert nz + k + 1 == len(v), 'hyper-parameter vector has the wrong length'
+        self.noise_var = float(v[nz + k])
+        self.update()
+
+    @staticmethod
+    def _chol(A):
+        L, info = lapack.dpotrf(np.ascontiguousarray(A), lower=1)
+        jitter, tries = np.diag(A).mean() * 1e-6, 0
+        while info != 0:
+            assert tries < 5, 'matrix not positive definite, even with jitter'
+            L, info = lapack.dpotrf(A + np.eye(len(A)) * jitter, lower=1)
+            jitter *= 10
+            tries += 1
+        return np.tril(L)
+
+    def update(self):
+        m = len(self.Z)
+        beta = 1.0 / max(self.noise_var, 1e-6)
+        Kmm = self.kern.K(self.Z)
+        Kmm[np.diag_indices(m)] += 1e-8
+        Lm = self._chol(Kmm)
+        psi1 = self.kern.K(self.X, self.Z)
+        half = psi1 * np.sqrt(beta)
+        LmInv, _ = lapack.dtrtri(Lm, lower=1)
+        A = LmInv.dot(half.T.dot(half).dot(LmInv.T))
+        LB = self._chol(np.eye(m) + A)
+        rhs = psi1.T.dot(beta * self.Y)
+        t, _ = lapack.dtrtrs(Lm, rhs, lower=1, trans=0)
+        t, _ = lapack.dtrtrs(LB, t, lower=1, trans=0)
+        t, _ = lapack.dtrtrs(LB, t, lower=1, trans=1)
+        wv, _ = lapack.dtrtrs(Lm, t, lower=1, trans=1)
+        Bi, _ = lapack.dpotri(LB, lower=1)
+        Bi = -(np.tril(Bi) + np.tril(Bi, -1).T)
+        Bi[np.diag_indices(m)] += 1.0
+        t, _ = lapack.dtrtrs(Lm, Bi, lower=1, trans=1)
+        W, _ = lapack.dtrtrs(Lm, t.T, lower=1, trans=1)
+        W = W.T
+        self.posterior = _SparsePosterior(0.5 * (W + W.T), wv)
+        self._predictive_variable = self.Z
+
+
+class _SparsePosterior:
+    def __init__(self, woodbury_inv, woodbury_vector):
+        self.woodbury_inv = woodbury_inv
+        self.woodbury_vector = woodbury_vector
+
+
+def lower_root_of(W):
+    """Lower-triangular T with W = T^T T for a symmetric positive (semi-)definite W: the Cholesky factor of the
+    index-reversed matrix, reversed back.  |T k|^2 = k^T W k, so T plays the role L^-1 plays for an exact GP."""
+    n = len(W)
+    Wr = np.ascontiguousarray(W[::-1, ::-1])
+    scale = max(np.diag(W).mean(), 1e-300)
+    jitter, info = 0.0, 1
+    for _ in range(8):
+        G, info = lapack.dpotrf(Wr + np.eye(n) * jitter, lower=1)
+        if info == 0:
+            break
+        jitter = scale * 1e-14 if jitter == 0.0 else jitter * 100
+    assert info == 0, 'woodbury_inv is not positive semi-definite'
+    return np.ascontiguousarray(np.tril(G)[::-1, ::-1].T)
+
+
 class GPState:
     """Plain-array snapshot of one trained GP in the reference's transformed units."""
 
     def __init__(self, kernel, dim_x, dim_p, x_active, var_x, ls_x, var_p, ls_p, Z, alpha, L,
-                 power_x=2.0, power_p=2.0):
+                 power_x=2.0, power_p=2.0, factor_kind=0):
         self.kernel = kernel
         self.dim_x, self.dim_p = int(dim_x), int(dim_p)
         self.x_active = np.ascontiguousarray(x_active, dtype=np.int32)
@@ -99,6 +188,7 @@ class GPState:
         self.ls_x = _lib.as_f64(np.ravel(ls_x))
         self.ls_p = _lib.as_f64(np.ravel(ls_p))
         self.power_x, self.power_p = float(power_x), float(power_p)
+        self.factor_kind = int(factor_kind)   # 0: L = chol(K + noise); 1: L = T with woodbury_inv = T^T T
         self.Z = _lib.as_f64(Z)
         self.alpha = _lib.as_f64(np.ravel(alpha))
         self.L = _lib.as_f64(L)
@@ -114,11 +204,16 @@ class GPState:
         assert kernels.kernel_name_of(kp) == name, 'both product parts share one class (gp_model.py:60)'
         p_dims = np.asarray(kp.active_dims, dtype=int)
         assert np.array_equal(p_dims, np.arange(dim_x, dim_x + dim_p)), 'kernp acts on columns D..D+P-1'
+        sparse = bool(getattr(gp, 'is_sparse', False)) or 'Sparse' in type(gp).__name__
+        if sparse:     # sparse_gp_model.py: posterior lives on the inducing inputs, only woodbury_inv is meaningful
+            factor, kind = lower_root_of(np.asarray(gp.posterior.woodbury_inv, dtype=float)), 1
+        else:
+            factor, kind = np.asarray(gp.posterior.woodbury_chol), 0
         return cls(name, dim_x, dim_p, np.asarray(kx.active_dims, dtype=int),
                    float(np.ravel(kx.variance)[0]), np.ravel(kx.lengthscale),
                    float(np.ravel(kp.variance)[0]), np.ravel(kp.lengthscale),
                    np.asarray(gp._predictive_variable), np.asarray(gp.posterior.woodbury_vector)[:, 0],
-                   np.asarray(gp.posterior.woodbury_chol),
+                   factor, factor_kind=kind,
                    power_x=float(np.ravel(getattr(kx, 'power', 2.0))[0]),
                    power_p=float(np.ravel(getattr(kp, 'power', 2.0))[0]))
 
@@ -133,6 +228,7 @@ class GPState:
         d.var_x, d.ls_x, d.power_x = self.var_x, dptr(self.ls_x), self.power_x
         d.var_p, d.ls_p, d.power_p = self.var_p, dptr(self.ls_p), self.power_p
         d.Z, d.alpha, d.L = dptr(self.Z), dptr(self.alpha), dptr(self.L)
+        d.factor_kind = self.factor_kind
         h = C.c_void_p()
         check(ctx.lib.gpd_gp_upload(ctx.handle, C.byref(d), C.byref(h)))
         return h

@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib, kernels
 from ._lib import check, dptr
 from .context import get_context
-from .gp_state import ExactGP, GPState, ProductKernel
+from .gp_state import ExactGP, GPState, ProductKernel, SparseGP
 
 
 class BoxTransform:
@@ -601,3 +601,37 @@ class GPModel:
             filename += '.gpdoemd.model'
         with open(filename, 'rb') as f:
             self._load_save_dict(pickle.load(f))
+
+
+class SparseGPModel(GPModel):
+    """``GPdoemd/models/sparse_gp_model.py:35-74``: GPModel whose surrogates are sparse GPs with at most
+    ``max_num_inducing`` inducing inputs.  Every hook is inherited: on the device a sparse GP is the same
+    computation as an exact one with the inducing inputs as "training rows", ``woodbury_vector`` as alpha and a
+    triangular root T of ``woodbury_inv`` in place of L^-1 (``GPD_FACTOR_ROOT``)."""
+
+    def __init__(self, model_dict, device=0):
+        super().__init__(model_dict, device=device)
+        self.max_num_inducing = model_dict.get('max_num_inducing', 500)
+
+    def gp_surrogate(self, Z=None, Y=None, kern_x=None, kern_p=None, num_inducing=None):
+        self.set_training_data(Z, Y)
+        assert self.Z is not None and self.Y is not None
+        self.set_kernels(kern_x, kern_p)
+        assert self.kern_x is not None and self.kern_p is not None
+        host_cls = kernels.BY_NAME[kernels.kernel_name_of(self.kern_x)]
+        R, J = binary_dimensions(self.Z, self.binary_variables)
+        numi = self.max_num_inducing if num_inducing is None else num_inducing
+        gps = []
+        for e in range(self.num_outputs):
+            gps.append([])
+            for r in R:
+                Jr = (J == r)
+                if not np.any(Jr):
+                    gps[e].append(None)
+                    continue
+                dim = self.dim_x + self.dim_p
+                kernx = host_cls(self.dim_x - self.dim_b, self.non_binary_variables, 'kernx')
+                kernp = host_cls(self.dim_p, range(self.dim_x, dim), 'kernp')
+                gps[e].append(SparseGP(self.Z[Jr], self.Y[np.ix_(Jr, [e])], ProductKernel(kernx, kernp),
+                                       num_inducing=numi, rng=np.random.default_rng(1000 * e + r)))
+        self.gps = gps

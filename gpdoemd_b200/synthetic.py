@@ -10,6 +10,8 @@ CONFIGS = {
     'C4': dict(M=8, E=8, D=3, P=10, n=4000, kernel='Matern52', order=1, criteria=('HR', 'BH', 'BF', 'AW', 'JR'),
                N=1000000),
     'C5': dict(M=4, E=4, D=3, P=4, n=4000, kernel='Matern52', order=1, criteria=('BH',), N=100000000),
+    # SparseGPModel surrogates (reference default max_num_inducing = 500) on the C2 shapes
+    'S2': dict(M=4, E=2, D=3, P=4, n=4000, inducing=500, kernel='RBF', order=1, criteria=('HR', 'BH'), N=100000),
 }
 
 
@@ -51,7 +53,8 @@ def candidates(seed, N, D, xlo, xhi, n_binary=0):
     return X
 
 
-def build_models(cls, seed, M, E, D, P, n, kernel, n_binary=0, kernel_lookup=None, gp_noise=1e-6, **kw):
+def build_models(cls, seed, M, E, D, P, n, kernel, n_binary=0, kernel_lookup=None, gp_noise=1e-6,
+                 num_inducing=None, **kw):
     """Instantiate ``cls`` (gpdoemd_b200.GPModel or an API-compatible class) for M rival models."""
     models, datas = [], []
     for m in range(M):
@@ -60,8 +63,14 @@ def build_models(cls, seed, M, E, D, P, n, kernel, n_binary=0, kernel_lookup=Non
         mo = cls({'name': 'm%d' % m, 'call': (lambda x, p: None), 'dim_x': D, 'dim_p': Pm, 'num_outputs': E,
                   'meas_noise_var': 0.01, 'binary_variables': d['binary']}, **kw)
         k = kernel if kernel_lookup is None else kernel_lookup[kernel]
-        mo.gp_surrogate(Z=d['Z'], Y=d['Y'], kern_x=k, kern_p=k)
-        mo.hyp = d['hyp']
+        if num_inducing is None:
+            mo.gp_surrogate(Z=d['Z'], Y=d['Y'], kern_x=k, kern_p=k)
+            mo.hyp = d['hyp']
+        else:
+            # sparse surrogates (cls = a SparseGPModel class): gp[:] starts with the inducing inputs
+            mo.gp_surrogate(Z=d['Z'], Y=d['Y'], kern_x=k, kern_p=k, num_inducing=num_inducing)
+            mo.hyp = [[None if gp is None else np.r_[np.ravel(gp.Z), h] for gp, h in zip(gps, hs)]
+                      for gps, hs in zip(mo.gps, d['hyp'])]
         mo.gp_load_hyp()
         mo.pmean = d['pmean']
         mo.Sigma = d['Sigma']

@@ -65,8 +65,14 @@ typedef struct gpd_gp_desc {
     double power_p;        /* kernp.power (RatQuad only) */
     const double* Z;       /* (n, D+P) gp._predictive_variable, transformed units */
     const double* alpha;   /* (n)      gp.posterior.woodbury_vector */
-    const double* L;       /* (n, n)   gp.posterior.woodbury_chol, lower triangle used */
+    const double* L;       /* (n, n)   lower triangle used; meaning given by factor_kind */
+    int32_t factor_kind;   /* GPD_FACTOR_CHOL: L = gp.posterior.woodbury_chol = chol(K + noise), the library forms
+                            *   L^-1 (exact GP, gp_model.py:123);
+                            * GPD_FACTOR_ROOT: L = T, lower triangular with gp.posterior.woodbury_inv = T^T T, used
+                            *   as is: variance = k** - |T k*|^2 (sparse GP, sparse_gp_model.py:35-74: n = number
+                            *   of inducing inputs, Z = gp._predictive_variable = the inducing inputs) */
 } gpd_gp_desc;
+enum gpd_factor_kind { GPD_FACTOR_CHOL = 0, GPD_FACTOR_ROOT = 1 };
 
 /* ---- context ----------------------------------------------------------------------------- */
 int  gpd_create(int device, gpd_ctx** out);

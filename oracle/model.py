@@ -10,6 +10,7 @@ import numpy as np
 
 from . import gpy_kernels
 from .gp import GPRegression
+from .sparse_gp import SparseGPRegression
 from .gpy_kernels import Prod
 from .routing import binary_dimensions
 from .transform import BoxTransform, MeanTransform
@@ -189,3 +190,35 @@ class OracleGPModel:
                 ddk = np.sum(kp.gradients_XX(-kx * kiK, Z, gpX), axis=1)[:, dx:, dx:]
                 dds2[I] = -2.0 * (ddk + dkiKdk)
         return dds2
+
+
+class OracleSparseGPModel(OracleGPModel):
+    """GPdoemd/models/sparse_gp_model.py:35-74: same hooks, GPy SparseGPRegression per output / binary combination."""
+
+    def __init__(self, model_dict):
+        super().__init__(model_dict)
+        self.max_num_inducing = model_dict.get('max_num_inducing', 500)
+
+    def gp_surrogate(self, Z=None, Y=None, kern_x=None, kern_p=None, num_inducing=None):
+        if Z is not None:
+            self.set_training_data(Z, Y)
+        assert self.Z is not None and self.Y is not None
+        kx = gpy_kernels.KERNELS[kern_x] if isinstance(kern_x, str) else kern_x
+        assert kx is not None and kern_p is not None
+        self.kern_x = kx
+        R, J = binary_dimensions(self.Z, self.binary_variables)
+        dim = self.dim_x + self.dim_p
+        numi = self.max_num_inducing if num_inducing is None else num_inducing
+        gps = []
+        for e in range(self.num_outputs):
+            gps.append([])
+            for r in R:
+                Jr = (J == r)
+                if not np.any(Jr):
+                    gps[e].append(None)
+                    continue
+                kernx = kx(self.dim_x - self.dim_b, self.non_binary_variables, 'kernx')
+                kernp = kx(self.dim_p, range(self.dim_x, dim), 'kernp')
+                gps[e].append(SparseGPRegression(self.Z[Jr], self.Y[np.ix_(Jr, [e])], Prod(kernx, kernp),
+                                                 num_inducing=numi, rng=np.random.default_rng(1000 * e + r)))
+        self.gps = gps

@@ -4,12 +4,17 @@ import numpy as np
 
 from gpdoemd_b200 import synthetic
 from oracle import gpy_kernels
-from oracle.model import OracleGPModel
+from oracle.model import OracleGPModel, OracleSparseGPModel
 
 
 def oracle_models(seed, M, E, D, P, n, kernel, n_binary=0, gp_noise=1e-6):
     return synthetic.build_models(OracleGPModel, seed, M, E, D, P, n, kernel, n_binary,
                                   kernel_lookup=gpy_kernels.KERNELS, gp_noise=gp_noise)
+
+
+def oracle_sparse_models(seed, M, E, D, P, n, kernel, num_inducing, n_binary=0, gp_noise=1e-4):
+    return synthetic.build_models(OracleSparseGPModel, seed, M, E, D, P, n, kernel, n_binary,
+                                  kernel_lookup=gpy_kernels.KERNELS, gp_noise=gp_noise, num_inducing=num_inducing)
 
 
 def gpu_models(oracle_ms):
