@@ -87,6 +87,7 @@ def main():
     t2 = load('ref_taylor_second_order', 'GPdoemd/marginal/taylor_second_order.py')
     tr = load('ref_transform', 'GPdoemd/transform.py')
     ut = load('ref_utils', 'GPdoemd/utils.py')
+    la = load('ref_laplace', 'GPdoemd/param_covar/laplace_approximation.py')
     out = {}
 
     # ---- criteria: notebook input (deterministic) ---------------------------------------------
@@ -137,6 +138,17 @@ def main():
         M2_, S2_ = t2.taylor_second_order(st, X)
         key = 'ty%d_%d_' % (E, P)
         out[key + 'X'], out[key + 'M1'], out[key + 'S1'], out[key + 'M2'], out[key + 'S2'] = X, M1_, S1_, M2_, S2_
+
+    # ---- Laplace approximation of the parameter covariance (param_covar/laplace_approximation.py) -------------
+    for (E, P) in ((1, 1), (2, 3), (3, 5)):
+        st = StubModel(E, P, 7 * E + P)
+        X = np.random.default_rng(6).uniform(-1, 1, (12, 2))
+        st.meas_noise_var = 0.01 * (1 + np.arange(E))
+        out['la%d_%d_diag' % (E, P)] = la.laplace_approximation(st, X)
+        B = np.random.default_rng(8).normal(size=(E, E))
+        st.meas_noise_var = 0.01 * np.eye(E) + 0.002 * B.dot(B.T)
+        out['la%d_%d_full' % (E, P)] = la.laplace_approximation(st, X)
+        out['la%d_%d_X' % (E, P)] = X
 
     # ---- transforms ---------------------------------------------------------------------------------------
     rng = np.random.default_rng(9)

@@ -350,3 +350,20 @@ def test_accuracy_vs_extended_precision(gpu_ctx):
         print('%-4s error vs 80-bit truth / scale: oracle %.2e  cuda %.2e' % (k, eo, eg))
         assert eg < 1e-9, (k, eg)
         assert eg < max(3 * eo, 1e-12), (k, eg, eo)
+
+
+def test_laplace_approximation_on_device_model(gpu_ctx):
+    """Sigma = laplace_approximation(model, Xobs) with the device d_mu_d_p hook vs the oracle model."""
+    import gpdoemd_b200 as g
+    oms, ds = helpers.oracle_models(71, M=1, E=2, D=3, P=3, n=200, kernel='Matern52')
+    gm = helpers.gpu_models(oms)[0]
+    Xobs = g.synthetic.candidates(4, 9, 3, ds[0]['xlo'], ds[0]['xhi'])
+    for mv in (np.array([0.01, 0.04]), np.array([[0.01, 0.002], [0.002, 0.03]])):
+        oms[0].meas_noise_var = mv
+        gm.meas_noise_var = mv
+        S0 = g.laplace_approximation(oms[0], Xobs)
+        S1 = g.laplace_approximation(gm, Xobs)
+        assert helpers.relerr(S1, S0, np.abs(S0).max()) < 1e-7
+        gm.Sigma = S1                      # and it feeds straight back into the marginal
+        M1, V1 = g.taylor_first_order(gm, Xobs)
+        assert np.all(np.isfinite(V1))

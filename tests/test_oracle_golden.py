@@ -117,3 +117,17 @@ def test_routing_vs_reference_run(nb):
     from gpdoemd_b200.models import binary_dimensions
     r2, j2 = binary_dimensions(Z, list(range(2, 2 + nb)))
     assert list(r2) == list(range(2 ** nb)) and np.array_equal(j2, J)
+
+
+@pytest.mark.parametrize('EP', [(1, 1), (2, 3), (3, 5)])
+def test_laplace_approximation_vs_reference(EP):
+    """gpdoemd_b200.laplace_approximation == GPdoemd/param_covar/laplace_approximation.py on a duck-typed model."""
+    from gpdoemd_b200 import laplace_approximation
+    E, P = EP
+    st = make_golden.StubModel(E, P, 7 * E + P)
+    X = G['la%d_%d_X' % (E, P)]
+    st.meas_noise_var = 0.01 * (1 + np.arange(E))
+    np.testing.assert_allclose(laplace_approximation(st, X), G['la%d_%d_diag' % (E, P)], rtol=1e-12)
+    B = np.random.default_rng(8).normal(size=(E, E))
+    st.meas_noise_var = 0.01 * np.eye(E) + 0.002 * B.dot(B.T)
+    np.testing.assert_allclose(laplace_approximation(st, X), G['la%d_%d_full' % (E, P)], rtol=1e-11)
