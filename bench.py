@@ -129,6 +129,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--tri-variant', type=int, default=None)
     ap.add_argument('--tri-cps', type=int, default=None)
+    ap.add_argument('--tri-trim', type=int, default=None)
     args = ap.parse_args()
     # ONE JSON line on stdout: libraries (NCCL prints its version banner there) are sent to stderr
     sys.stdout.flush()
@@ -177,6 +178,8 @@ def main():
         ctx.set_option('tri_variant', args.tri_variant)
     if args.tri_cps is not None:
         ctx.set_option('tri_cps', args.tri_cps)
+    if args.tri_trim is not None:
+        ctx.set_option('tri_trim', args.tri_trim)
     if (cfg.get('inducing') or cfg['n']) >= 2000:
         ctx.set_scratch_bytes(64 << 30)
 

@@ -56,6 +56,7 @@ struct gpd_ctx {
     uint64_t launches = 0;
     int tri_variant = 0;
     int tri_cps = 0;   // 0 = automatic (by factor size), 1 or 2 = forced chunks per pipeline stage
+    int tri_trim = 1;  // skip the all-padding 8-row blocks of the last row block
     // profiling: event pairs recorded without synchronising, resolved in gpd_profile_read
     int profile = 0;
     struct Span { cudaEvent_t a, b; int fam; };
@@ -438,7 +439,8 @@ static int run_chunk(gpd_ctx* c, Plan& pl, const double* X_dev, int ldx, int nc)
     if (!pl.need_W) {
         Span sp(c, F_TRI, 1, n2sum);
         GPD_TRY(launch_tri(s, pl.views_dev, pl.items_dev, pl.nitems, 1, 1, 1, 0, pl.panels_in, nullptr, pl.raws_dev,
-                           tri_row_groups(c->tri_variant), nc, c->num_sms, c->tri_variant, tri_cps_for(c, pl)));
+                           tri_row_groups(c->tri_variant), nc, c->num_sms, c->tri_variant, tri_cps_for(c, pl),
+                           c->tri_trim));
     } else {
         for (auto& grp : pl.groups) {
             const int nrhs = 1 + grp.P;
@@ -452,7 +454,8 @@ static int run_chunk(gpd_ctx* c, Plan& pl, const double* X_dev, int ldx, int nc)
             {
                 Span sp(c, F_TRI, 1, fl);
                 GPD_TRY(launch_tri(s, pl.views_dev, pl.items_dev + grp.item_begin, grp.item_count, nrhs, nrhs, nrhs, 0,
-                                   pl.panels_in, pl.panels_out, nullptr, 0, nc, c->num_sms, c->tri_variant, tri_cps_for(c, pl)));
+                                   pl.panels_in, pl.panels_out, nullptr, 0, nc, c->num_sms, c->tri_variant, tri_cps_for(c, pl),
+                                   c->tri_trim));
             }
             {
                 Span sp(c, F_GRAM, 1, fl / (double)std::max(1, pl.entries[grp.entries[0]].gp->n) * (nrhs + 1));
@@ -463,7 +466,8 @@ static int run_chunk(gpd_ctx* c, Plan& pl, const double* X_dev, int ldx, int nc)
                 {
                     Span sp(c, F_TRI, 1, flb);
                     GPD_TRY(launch_tri(s, pl.views_dev, pl.items_dev + grp.item_begin, grp.item_count, 1, nrhs, 1, 1,
-                                       pl.panels_out, pl.panels_beta, nullptr, 0, nc, c->num_sms, c->tri_variant, tri_cps_for(c, pl)));
+                                       pl.panels_out, pl.panels_beta, nullptr, 0, nc, c->num_sms, c->tri_variant, tri_cps_for(c, pl),
+                                       0));
                 }
                 Span sp(c, F_EVAL, 1, 0);
                 GPD_TRY(launch_beta_contract(s, pl.views_dev, pl.items_dev + grp.item_begin, grp.item_count, X_dev, ldx, nc,
@@ -476,7 +480,7 @@ static int run_chunk(gpd_ctx* c, Plan& pl, const double* X_dev, int ldx, int nc)
         ModelBufs& b = pl.mb[m];
         Span sp(c, F_MARG, 1, 0);
         GPD_TRY(launch_finalize(s, mo->xf_dev + (pl.transformed ? 1 : 0), pl.raws_dev, m, mo->E, mo->P, nc, b.ldraw, pl.flags,
-                                pl.need_W ? 1 + mo->P : 1, pl.need_W ? 0 : tri_row_groups(c->tri_variant), b.mu, b.ldmu,
+                                pl.need_W ? 1 + mo->P : 1, pl.need_W ? 0 : b.ng, b.mu, b.ldmu,
                                 b.s2, b.dmu, b.d2mu, b.ds2, b.d2s2));
     }
     return 0;
@@ -564,6 +568,11 @@ int gpd_set_option(gpd_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "tri_cps")) {
         GPD_CHECK(value >= 0 && value <= 2, "tri_cps is 0 (automatic), 1 or 2");
         c->tri_cps = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "tri_trim")) {
+        GPD_CHECK(value == 0 || value == 1, "tri_trim is 0 or 1");
+        c->tri_trim = (int)value;
         return 0;
     }
     set_error(std::string("unknown option ") + name);

@@ -101,7 +101,7 @@ int launch_invert_and_pack(cudaStream_t s, const double* L_dev, int n, int n_pad
                            double* packF, double* packB, uint64_t* launches, int factor_kind);
 int launch_tri(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int nitems, int nwork_rhs,
                int in_stride, int out_stride, int backward, const double* panels_in, double* panels_out,
-               const RawOut* raw_dev, int ng, int chunk_n, int num_sms, int variant, int cps);
+               const RawOut* raw_dev, int ng, int chunk_n, int num_sms, int variant, int cps, int trim);
 int launch_gram(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int nitems, int nrhs,
                 const double* panels, const RawOut* raw_dev, int chunk_n);
 int launch_dmma_probe(cudaStream_t s, int num_sms, int iters, double* sink_dev);

@@ -99,6 +99,7 @@ struct TriArgs {
     const RawOut* raws;   // non-null: write column sums of squares into raw.gram[..][0]
     int ng;               // row length of raw.gram
     int chunk_n;
+    int trim;             // skip the all-padding 8-row blocks of the last row block (forward, 16-warp variant)
 };
 
 // One k4 step for the 8-row blocks [LO, HI) of this warp's row group.
@@ -125,7 +126,7 @@ __device__ __forceinline__ void kstep_bounded(int v, double (&acc)[MB][NB][2], c
     }
 }
 
-template <int WM, int WN, bool DIAG, bool BWD>
+template <int WM, int WN, bool DIAG, bool BWD, int HI = 16 / WM>
 __device__ __forceinline__ void compute_chunk(const double* __restrict__ sA, const double* __restrict__ sB, int lane,
                                               int wm, int wn, int chunk_in_blk,
                                               double (&acc)[16 / WM][16 / WN][2]) {
@@ -146,13 +147,14 @@ __device__ __forceinline__ void compute_chunk(const double* __restrict__ sA, con
     for (int kp = 0; kp < 2; ++kp) {
         double2 a2[MB];
 #pragma unroll
-        for (int mb = 0; mb < MB; ++mb) a2[mb] = *reinterpret_cast<const double2*>(pa + (GPD_BLK(wm, mb, WM, MB) * 2 + kp) * 64);
+        for (int mb = 0; mb < MB; ++mb)
+            if (mb < HI) a2[mb] = *reinterpret_cast<const double2*>(pa + (GPD_BLK(wm, mb, WM, MB) * 2 + kp) * 64);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int ks = kp * 2 + h;
             double a[MB], b[NB];
 #pragma unroll
-            for (int mb = 0; mb < MB; ++mb) a[mb] = h ? a2[mb].y : a2[mb].x;
+            for (int mb = 0; mb < MB; ++mb) a[mb] = (mb < HI) ? (h ? a2[mb].y : a2[mb].x) : 0.0;
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb) b[nb] = ((nb & 1) ? pb1 : pb0)[ks * 4 * kBlk + (nb >> 1) * 16];
             if (DIAG) {
@@ -170,7 +172,7 @@ __device__ __forceinline__ void compute_chunk(const double* __restrict__ sA, con
                 v = v > MB ? MB : v;
                 kstep_bounded<MB, NB, BWD, 0>(v, acc, a, b);
             } else {
-                kstep<MB, NB, 0, MB>(acc, a, b);
+                kstep<MB, NB, 0, HI>(acc, a, b);
             }
         }
     }
@@ -246,6 +248,7 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) tri_kernel(const TriArgs args
     constexpr int kStages = TriCfg<CPS>::kStages;
     constexpr int kCps = CPS;
     constexpr int MB = 16 / WM, NB = 16 / WN;
+    constexpr bool kTrimOk = !BWD && MB == 4 && !GPD_TRI_CYCLIC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TriSmem<CPS>& sm = *reinterpret_cast<TriSmem<CPS>*>(smem_raw);
 
@@ -304,6 +307,16 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) tri_kernel(const TriArgs args
                 for (int nb = 0; nb < NB; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
             const int len = tile_run_len(nblk, I, BWD);
             const int qdiag = BWD ? 0 : len - 1;
+            // Dense-tile mode of this warp in this row block.  Rows n..n_pad are padding (their v is zero): in the
+            // last row block a warp runs only its `hi` 8-row blocks that hold training rows (mode 2 + hi), or
+            // nothing.  Every SMSP hosts all row groups, so the saving is spread over the four tensor pipes.
+            // The diagonal tile keeps the full path.
+            int mode_dense = 1;
+            if (kTrimOk && args.trim && I == nblk - 1) {
+                const int left = g.n - I * kBlk - wm * (MB * 8);
+                const int hi = left <= 0 ? 0 : (left >= MB * 8 ? MB : (left + 7) >> 3);
+                mode_dense = hi == MB ? 1 : (hi == 0 ? 0 : 2 + hi);
+            }
 #pragma unroll 1
             for (int q = 0; q < len; ++q) {
                 const bool diag = (q == qdiag);
@@ -315,7 +328,7 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) tri_kernel(const TriArgs args
                         const double* sA = sm.A[stage] + cc * kChunkElems;
                         const double* sB = sm.B[stage] + cc * kChunkElems;
                         // this warp's rows against this chunk's k range: dense, all zero, or straddling the diagonal
-                        int mode = 1;
+                        int mode = mode_dense;
                         if (diag) {
                             const int rlo = GPD_BLK(wm, 0, WM, MB) * 8, rhi = GPD_BLK(wm, MB - 1, WM, MB) * 8 + 7;
                             const int klo = (c + cc) * kChunkK, khi = klo + kChunkK - 1;
@@ -325,6 +338,9 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) tri_kernel(const TriArgs args
                         }
                         if (mode == 1) compute_chunk<WM, WN, false, BWD>(sA, sB, lane, wm, wn, c + cc, acc);
                         else if (mode == 2) compute_chunk<WM, WN, true, BWD>(sA, sB, lane, wm, wn, c + cc, acc);
+                        else if (kTrimOk && mode == 3) compute_chunk<WM, WN, false, BWD, 1>(sA, sB, lane, wm, wn, c + cc, acc);
+                        else if (kTrimOk && mode == 4) compute_chunk<WM, WN, false, BWD, (MB > 2 ? 2 : 1)>(sA, sB, lane, wm, wn, c + cc, acc);
+                        else if (kTrimOk && mode == 5) compute_chunk<WM, WN, false, BWD, (MB > 3 ? 3 : 1)>(sA, sB, lane, wm, wn, c + cc, acc);
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stage]));
@@ -395,7 +411,7 @@ static int tri_launch_one(cudaStream_t s, int grid, const TriArgs& args) {
 
 int launch_tri(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int nitems, int nwork_rhs,
                int in_stride, int out_stride, int backward, const double* panels_in, double* panels_out,
-               const RawOut* raw_dev, int ng, int chunk_n, int num_sms, int variant, int cps) {
+               const RawOut* raw_dev, int ng, int chunk_n, int num_sms, int variant, int cps, int trim) {
     if (nitems == 0) return 0;
     TriArgs args;
     args.gps = gps_dev;
@@ -410,6 +426,7 @@ int launch_tri(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int
     args.raws = raw_dev;
     args.ng = ng;
     args.chunk_n = chunk_n;
+    args.trim = trim;
     long long nwork = (long long)nitems * nwork_rhs;
     int grid = (int)(nwork < num_sms ? nwork : num_sms);
 #define GPD_TRI_GO(WM, BWD, CPS) return tri_launch_one<WM, 4, BWD, CPS>(s, grid, args)

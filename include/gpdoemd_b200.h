@@ -81,7 +81,8 @@ const char* gpd_last_error(void);
 /* bytes of per-context scratch the fused paths may use for the K(x*,X) / L^-1 K panels (default 6 GiB) */
 int  gpd_set_scratch_bytes(gpd_ctx* ctx, uint64_t bytes);
 /* tuning knobs: "tri_variant" 0 = 16 warps (32x32 warp tiles), 1 = 8 warps (64x32);
- * "tri_cps" 0 = automatic, 1 = 4 pipeline stages of 16 k, 2 = 3 stages of 32 k */
+ * "tri_cps" 0 = automatic, 1 = 4 pipeline stages of 16 k, 2 = 3 stages of 32 k;
+ * "tri_trim" 1 (default) = the all-padding 8-row blocks (rows n..n_pad) of the last row block are skipped */
 int  gpd_set_option(gpd_ctx* ctx, const char* name, int64_t value);
 /* number of CUDA kernels launched by this context so far (bench.py `gpu_launches`) */
 uint64_t gpd_launch_count(gpd_ctx* ctx);
