@@ -8,12 +8,12 @@ or device is missing (there is no CPU fallback).
 from . import design_criteria, kernels, marginal, scoring, synthetic
 from .context import Context, get_context
 from .design_criteria import AW, BF, BH, HR, JR
-from .gp_state import ExactGP, GPState, SparseGP
+from .gp_state import DeviceExactGP, ExactGP, GPState, SparseGP
 from .marginal import taylor_first_order, taylor_second_order
 from .models import GPModel, SparseGPModel
 from .param_covar import laplace_approximation
 from .scoring import ShardedScorer, score_designs, score_designs_dev, score_designs_multi
 
-__all__ = ['GPModel', 'SparseGPModel', 'GPState', 'ExactGP', 'SparseGP', 'Context', 'get_context', 'kernels', 'marginal', 'design_criteria',
+__all__ = ['GPModel', 'SparseGPModel', 'GPState', 'ExactGP', 'DeviceExactGP', 'SparseGP', 'Context', 'get_context', 'kernels', 'marginal', 'design_criteria',
            'scoring', 'taylor_first_order', 'taylor_second_order', 'laplace_approximation', 'HR', 'BH', 'BF', 'AW', 'JR', 'score_designs',
            'score_designs_dev', 'score_designs_multi', 'ShardedScorer', 'synthetic']

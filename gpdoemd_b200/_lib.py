@@ -47,6 +47,8 @@ _SIGNATURES = {
     'gpd_probe_fp64_peak': (C.c_int, [C.c_void_p, c_double_p]),
     'gpd_flush_l2': (C.c_int, [C.c_void_p]),
     'gpd_gp_upload': (C.c_int, [C.c_void_p, C.POINTER(GpDesc), c_void_pp]),
+    'gpd_gp_build': (C.c_int, [C.c_void_p, C.POINTER(GpDesc), c_double_p, C.c_double, c_void_pp, c_double_p, c_double_p,
+                               c_double_p]),
     'gpd_gp_free': (None, [C.c_void_p]),
     'gpd_model_create': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_int32_p, c_void_pp,
                                    c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_void_pp]),

@@ -745,16 +745,19 @@ void gpd_gp_free(gpd_gp* g) {
     delete g;
 }
 
-int gpd_gp_upload(gpd_ctx* c, const gpd_gp_desc* d, gpd_gp** out) {
-    GPD_CHECK(c && d && out, "null argument");
+}  // extern "C"
+
+namespace gpd {
+// Shared part of gpd_gp_upload / gpd_gp_build: validation, allocation, upload of the scaled training inputs.
+// alpha and the packed factor are filled in by the caller.
+static int gp_create_common(gpd_ctx* c, const gpd_gp_desc* d, gpd_gp** out) {
     *out = nullptr;
     GPD_CHECK(d->kernel >= 0 && d->kernel <= 5, "unknown kernel id");
-    GPD_CHECK(d->factor_kind == GPD_FACTOR_CHOL || d->factor_kind == GPD_FACTOR_ROOT, "unknown factor_kind");
     GPD_CHECK(d->n >= 1, "empty training set");
     GPD_CHECK(d->dim_p >= 1 && d->dim_p <= kMaxP, "dim_p out of range (1..16)");
     GPD_CHECK(d->n_x_active >= 1 && d->n_x_active <= kMaxXDims, "x-kernel acts on 1..8 non-binary design dimensions");
     GPD_CHECK(d->dim_x >= d->n_x_active, "dim_x smaller than the number of active dimensions");
-    GPD_CHECK(d->x_active && d->ls_x && d->ls_p && d->Z && d->alpha && d->L, "null array in descriptor");
+    GPD_CHECK(d->x_active && d->ls_x && d->ls_p && d->Z, "null array in descriptor");
     GPD_CUDA(cudaSetDevice(c->device));
     gpd_gp* g = new gpd_gp();
     g->ctx = c;
@@ -779,6 +782,12 @@ int gpd_gp_upload(gpd_ctx* c, const gpd_gp_desc* d, gpd_gp** out) {
             return 2;
         }
     }
+    for (int a = 0; a < P; ++a)
+        if (!(d->ls_p[a] > 0)) {
+            delete g;
+            set_error("non-positive parameter lengthscale");
+            return 2;
+        }
     const int npair = P * (P + 1) / 2;
     std::vector<double> Xs((size_t)n_pad * nx, 0.0), Zp((size_t)n * P);
     for (int i = 0; i < n; ++i) {
@@ -786,56 +795,162 @@ int gpd_gp_upload(gpd_ctx* c, const gpd_gp_desc* d, gpd_gp** out) {
         for (int a = 0; a < P; ++a) Zp[(size_t)i * P + a] = d->Z[(size_t)i * dz + g->D + a];
     }
     cudaStream_t s = c->stream;
-    int rc = 0;
-    auto fail = [&](int code) {
-        gpd_gp_free(g);
-        return code;
-    };
-#define GP_CUDA(call)                                                                       \
-    do {                                                                                    \
-        cudaError_t e__ = (call);                                                           \
-        if (e__ != cudaSuccess) {                                                           \
-            set_error(std::string(#call) + ": " + cudaGetErrorString(e__));                 \
-            return fail(1);                                                                 \
-        }                                                                                   \
-    } while (0)
-    GP_CUDA(cudaMalloc(&g->Xs, sizeof(double) * Xs.size()));
-    GP_CUDA(cudaMalloc(&g->Zp, sizeof(double) * Zp.size()));
-    GP_CUDA(cudaMalloc(&g->alpha, sizeof(double) * n));
-    GP_CUDA(cudaMalloc(&g->ls_p, sizeof(double) * P));
-    GP_CUDA(cudaMalloc(&g->C, sizeof(double) * (size_t)(1 + P + npair) * n_pad));
-    GP_CUDA(cudaMalloc(&g->G, sizeof(double) * (size_t)(1 + P) * n_pad));
-    GP_CUDA(cudaMalloc(&g->H, sizeof(double) * (size_t)std::max(1, npair) * n_pad));
     const size_t pack_bytes = sizeof(double) * (size_t)packed_tiles(g->nblk) * kTileElems;
-    GP_CUDA(cudaMalloc(&g->LinvF, pack_bytes));
-    GP_CUDA(cudaMalloc(&g->LinvB, pack_bytes));
-    GP_CUDA(cudaMemcpyAsync(g->Xs, Xs.data(), sizeof(double) * Xs.size(), cudaMemcpyHostToDevice, s));
-    GP_CUDA(cudaMemcpyAsync(g->Zp, Zp.data(), sizeof(double) * Zp.size(), cudaMemcpyHostToDevice, s));
-    GP_CUDA(cudaMemcpyAsync(g->alpha, d->alpha, sizeof(double) * n, cudaMemcpyHostToDevice, s));
-    GP_CUDA(cudaMemcpyAsync(g->ls_p, d->ls_p, sizeof(double) * P, cudaMemcpyHostToDevice, s));
-    // factor: upload L, invert on the device, pack forward and backward operands
-    double *L_dev = nullptr, *dense = nullptr;
-    GP_CUDA(cudaMalloc(&L_dev, sizeof(double) * (size_t)n * n));
-    if (cudaMalloc(&dense, sizeof(double) * (size_t)n_pad * n_pad) != cudaSuccess) {
-        cudaFree(L_dev);
+    cudaError_t e = cudaMalloc(&g->Xs, sizeof(double) * Xs.size());
+    if (e == cudaSuccess) e = cudaMalloc(&g->Zp, sizeof(double) * Zp.size());
+    if (e == cudaSuccess) e = cudaMalloc(&g->alpha, sizeof(double) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&g->ls_p, sizeof(double) * P);
+    if (e == cudaSuccess) e = cudaMalloc(&g->C, sizeof(double) * (size_t)(1 + P + npair) * n_pad);
+    if (e == cudaSuccess) e = cudaMalloc(&g->G, sizeof(double) * (size_t)(1 + P) * n_pad);
+    if (e == cudaSuccess) e = cudaMalloc(&g->H, sizeof(double) * (size_t)std::max(1, npair) * n_pad);
+    if (e == cudaSuccess) e = cudaMalloc(&g->LinvF, pack_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&g->LinvB, pack_bytes);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(g->Xs, Xs.data(), sizeof(double) * Xs.size(), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(g->Zp, Zp.data(), sizeof(double) * Zp.size(), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(g->ls_p, d->ls_p, sizeof(double) * P, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);      // Xs / Zp are host temporaries
+    if (e != cudaSuccess) {
+        set_error(std::string("GP state allocation / upload failed: ") + cudaGetErrorString(e));
+        gpd_gp_free(g);
+        return 1;
+    }
+    *out = g;
+    return 0;
+}
+
+// L_dev (n x n row-major, lower triangle) -> packed forward / backward operands of the triangular kernel
+static int gp_pack_factor(gpd_ctx* c, gpd_gp* g, const double* L_dev, int factor_kind) {
+    double* dense = nullptr;
+    if (cudaMalloc(&dense, sizeof(double) * (size_t)g->n_pad * g->n_pad) != cudaSuccess) {
         set_error("out of device memory for the factor inversion workspace");
-        return fail(1);
+        return 1;
     }
-    cudaError_t e1 = cudaMemcpyAsync(L_dev, d->L, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, s);
-    if (e1 == cudaSuccess) {
-        uint64_t nl = 0;
-        rc = launch_invert_and_pack(s, L_dev, n, n_pad, dense, g->LinvF, g->LinvB, &nl, d->factor_kind);
-        c->launches += nl;
-        if (c->profile) c->fam_launches[F_SETUP] += nl;
-    }
-    cudaError_t e2 = cudaStreamSynchronize(s);
-    cudaFree(L_dev);
+    uint64_t nl = 0;
+    int rc = launch_invert_and_pack(c->stream, L_dev, g->n, g->n_pad, dense, g->LinvF, g->LinvB, &nl, factor_kind);
+    c->launches += nl;
+    if (c->profile) c->fam_launches[F_SETUP] += nl;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
     cudaFree(dense);
-    if (e1 != cudaSuccess || e2 != cudaSuccess || rc) {
-        if (!rc) set_error(std::string("factor upload/inversion failed: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-        return fail(1);
+    if (rc) return rc;
+    if (e != cudaSuccess) {
+        set_error(std::string("factor inversion failed: ") + cudaGetErrorString(e));
+        return 1;
     }
-#undef GP_CUDA
+    return 0;
+}
+}  // namespace gpd
+
+extern "C" {
+
+int gpd_gp_upload(gpd_ctx* c, const gpd_gp_desc* d, gpd_gp** out) {
+    GPD_CHECK(c && d && out, "null argument");
+    *out = nullptr;
+    GPD_CHECK(d->factor_kind == GPD_FACTOR_CHOL || d->factor_kind == GPD_FACTOR_ROOT, "unknown factor_kind");
+    GPD_CHECK(d->alpha && d->L, "null array in descriptor");
+    gpd_gp* g = nullptr;
+    GPD_TRY(gp_create_common(c, d, &g));
+    const int n = g->n;
+    cudaStream_t s = c->stream;
+    double* L_dev = nullptr;
+    cudaError_t e = cudaMalloc(&L_dev, sizeof(double) * (size_t)n * n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(g->alpha, d->alpha, sizeof(double) * n, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(L_dev, d->L, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, s);
+    int rc = 0;
+    if (e == cudaSuccess) rc = gp_pack_factor(c, g, L_dev, d->factor_kind);
+    else set_error(std::string("factor upload failed: ") + cudaGetErrorString(e));
+    cudaStreamSynchronize(s);
+    cudaFree(L_dev);
+    if (e != cudaSuccess || rc) {
+        gpd_gp_free(g);
+        return rc ? rc : 1;
+    }
+    *out = g;
+    return 0;
+}
+
+int gpd_gp_build(gpd_ctx* c, const gpd_gp_desc* d, const double* Y, double noise_var, gpd_gp** out, double* alpha_out,
+                 double* L_out, double* jitter_out) {
+    GPD_CHECK(c && d && Y && out, "null argument");
+    *out = nullptr;
+    GPD_CHECK(d->factor_kind == GPD_FACTOR_CHOL, "gpd_gp_build forms the Cholesky factor of an exact GP");
+    GPD_CHECK(noise_var >= 0.0, "negative noise variance");
+    gpd_gp* g = nullptr;
+    GPD_TRY(gp_create_common(c, d, &g));
+    const int n = g->n, dz = g->D + g->P;
+    cudaStream_t s = c->stream;
+    double *A = nullptr, *Z_dev = nullptr, *y_dev = nullptr;
+    int* info_dev = nullptr;
+    int rc = 0;
+    double jitter = 0.0;
+    cudaError_t e = cudaMalloc(&A, sizeof(double) * (size_t)n * n);
+    if (e == cudaSuccess) e = cudaMalloc(&Z_dev, sizeof(double) * (size_t)n * dz);
+    if (e == cudaSuccess) e = cudaMalloc(&y_dev, sizeof(double) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&info_dev, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(Z_dev, d->Z, sizeof(double) * (size_t)n * dz, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(y_dev, Y, sizeof(double) * n, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        KmatArgs ka;
+        memset(&ka, 0, sizeof(ka));
+        ka.kernel = g->kernel;
+        ka.n = n;
+        ka.dz = dz;
+        ka.D = g->D;
+        ka.P = g->P;
+        ka.nx = g->nx;
+        for (int k = 0; k < g->nx; ++k) {
+            ka.x_active[k] = g->x_active[k];
+            ka.ls_x[k] = g->ls_x[k];
+        }
+        for (int a = 0; a < g->P; ++a) ka.ls_p[a] = d->ls_p[a];
+        ka.var_x = g->var_x;
+        ka.var_p = g->var_p;
+        ka.power_x = g->power_x;
+        ka.power_p = g->power_p;
+        // GPy jitchol: plain factorisation first, then up to 5 retries with
+        // jitter = mean(diag) * 1e-6, * 10 per retry
+        const double diag_mean = g->var_x * g->var_p + noise_var + 1e-8;
+        for (int attempt = 0; attempt <= 5 && !rc && e == cudaSuccess; ++attempt) {
+            jitter = attempt == 0 ? 0.0 : diag_mean * 1e-6 * pow(10.0, attempt - 1);
+            ka.diag_add = noise_var + 1e-8 + jitter;
+            const int init = n + 1;
+            e = cudaMemcpyAsync(info_dev, &init, sizeof(int), cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) break;
+            uint64_t nl = 1;
+            rc = launch_kmat(s, ka, Z_dev, A);
+            if (!rc) rc = launch_cholesky(s, A, n, info_dev, &nl);
+            c->launches += nl;
+            if (c->profile) c->fam_launches[F_SETUP] += nl;
+            if (rc) break;
+            int info = 0;
+            e = cudaMemcpyAsync(&info, info_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) break;
+            if (info > n) break;                 // positive definite
+            if (attempt == 5) {
+                set_error("covariance matrix not positive definite, even with jitter (GPy jitchol gives up after 5 tries)");
+                rc = 4;
+            }
+        }
+    }
+    if (e == cudaSuccess && !rc) {
+        rc = launch_chol_solve(s, A, n, y_dev, g->alpha);
+        c->launches += 1;
+        if (!rc && alpha_out) e = cudaMemcpyAsync(alpha_out, g->alpha, sizeof(double) * n, cudaMemcpyDeviceToHost, s);
+        if (!rc && e == cudaSuccess && L_out)
+            e = cudaMemcpyAsync(L_out, A, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, s);
+        if (!rc && e == cudaSuccess) rc = gp_pack_factor(c, g, A, GPD_FACTOR_CHOL);
+    }
+    if (e != cudaSuccess && !rc) set_error(std::string("device GP build failed: ") + cudaGetErrorString(e));
+    cudaStreamSynchronize(s);
+    cudaFree(A);
+    cudaFree(Z_dev);
+    cudaFree(y_dev);
+    cudaFree(info_dev);
+    if (e != cudaSuccess || rc) {
+        gpd_gp_free(g);
+        return rc ? rc : 1;
+    }
+    if (jitter_out) *jitter_out = jitter;
     *out = g;
     return 0;
 }

@@ -61,6 +61,14 @@ struct PostModel {               // per model slot of a fused scoring call (devi
     int P, ldraw, npart;
 };
 
+struct KmatArgs {                // covariance-matrix build of one GP (kernels_build.cu)
+    int kernel, n, dz, D, P, nx;
+    int x_active[kMaxXDims];
+    double ls_x[kMaxXDims], ls_p[kMaxP];
+    double var_x, var_p, power_x, power_p;
+    double diag_add;             // Gaussian noise variance + GPy's 1e-8 (+ jitchol jitter)
+};
+
 void set_error(const std::string& msg);
 #define GPD_CUDA(call)                                                                        \
     do {                                                                                      \
@@ -105,6 +113,10 @@ int launch_tri(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int
 int launch_gram(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int nitems, int nrhs,
                 const double* panels, const RawOut* raw_dev, int chunk_n);
 int launch_dmma_probe(cudaStream_t s, int num_sms, int iters, double* sink_dev);
+// kernels_build.cu
+int launch_kmat(cudaStream_t s, const KmatArgs& a, const double* Z_dev, double* A_dev);
+int launch_cholesky(cudaStream_t s, double* A_dev, int n, int* info_dev, uint64_t* launches);
+int launch_chol_solve(cudaStream_t s, const double* L_dev, int n, const double* y_dev, double* x_dev);
 // kernels_crit.cu
 int launch_route(cudaStream_t s, const double* X_dev, int ldx, int chunk_n, int nb, const int* bcols,
                  const int* weights, int ncombo, int* idx, int* counts, int idx_stride);

@@ -545,40 +545,46 @@ __global__ void __launch_bounds__(kBlk) diag_inv_kernel(const double* __restrict
     }
 }
 
-// X_JK = -D_J * sum_{m=K}^{J-1} L_Jm X_mK   for one block row J; CTA = (K, 32-column slab)
-__global__ void __launch_bounds__(256) offdiag_kernel(const double* __restrict__ L, int n, int n_pad, int J,
+// X_JK = -D_J * sum_{m=K}^{J-1} L_Jm X_mK.  The 32-column slabs of X are independent of each other (column c of
+// L^-1 solves L x = e_c), so one CTA = (block column K, slab) walks down ALL block rows J = K+1 .. nblk-1 in a
+// single launch, reading back the rows of its own slab it wrote in earlier iterations: nblk * 4 CTAs run
+// concurrently instead of one launch of J * 4 CTAs per block row.
+__global__ void __launch_bounds__(256) offdiag_kernel(const double* __restrict__ L, int n, int n_pad, int nblk,
                                                       double* __restrict__ X) {
     __shared__ double T[kBlk][33];
     const int K = blockIdx.x, slab = blockIdx.y;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // ty: 16 rows each
     const int col = K * kBlk + slab * 32 + tx;
-    const int r0 = J * kBlk;
-    double acc[16];
+    for (int J = K + 1; J < nblk; ++J) {
+        const int r0 = J * kBlk;
+        double acc[16];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) acc[r] = 0.0;
-    // columns of X_mK below the diagonal of block K are zero for rows < col: start at the slab's first column
-    const int kbeg = K * kBlk + slab * 32, kend = J * kBlk;
-    for (int k = kbeg; k < kend; ++k) {
-        const double xv = X[(size_t)k * n_pad + col];
+        for (int r = 0; r < 16; ++r) acc[r] = 0.0;
+        // columns of X_mK below the diagonal of block K are zero for rows < col: start at the slab's first column
+        const int kbeg = K * kBlk + slab * 32, kend = J * kBlk;
+        for (int k = kbeg; k < kend; ++k) {
+            const double xv = X[(size_t)k * n_pad + col];
 #pragma unroll
-        for (int r = 0; r < 16; ++r) acc[r] = fma(L_at(L, n, r0 + ty * 16 + r, k), xv, acc[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < 16; ++r) T[ty * 16 + r][tx] = acc[r];
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < 16; ++r) acc[r] = 0.0;
-    const int imax = ty * 16 + 15;
-    for (int m = 0; m <= imax; ++m) {
-        const double tv = T[m][tx];
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            const int i = ty * 16 + r;
-            if (m <= i) acc[r] = fma(X[(size_t)(r0 + i) * n_pad + r0 + m], tv, acc[r]);
+            for (int r = 0; r < 16; ++r) acc[r] = fma(L_at(L, n, r0 + ty * 16 + r, k), xv, acc[r]);
         }
-    }
 #pragma unroll
-    for (int r = 0; r < 16; ++r) X[(size_t)(r0 + ty * 16 + r) * n_pad + col] = -acc[r];
+        for (int r = 0; r < 16; ++r) T[ty * 16 + r][tx] = acc[r];
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 16; ++r) acc[r] = 0.0;
+        const int imax = ty * 16 + 15;
+        for (int m = 0; m <= imax; ++m) {
+            const double tv = T[m][tx];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int i = ty * 16 + r;
+                if (m <= i) acc[r] = fma(X[(size_t)(r0 + i) * n_pad + r0 + m], tv, acc[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 16; ++r) X[(size_t)(r0 + ty * 16 + r) * n_pad + col] = -acc[r];
+        __syncthreads();     // rows r0.. of this slab are read by the next block row; T is reused
+    }
 }
 
 __global__ void __launch_bounds__(256) pack_kernel(const double* __restrict__ X, int n_pad, int nblk, int backward,
@@ -624,8 +630,8 @@ int launch_invert_and_pack(cudaStream_t s, const double* L_dev, int n, int n_pad
         diag_inv_kernel<<<nblk, kBlk, 0, s>>>(L_dev, n, n_pad, dense_tmp);
         GPD_CUDA(cudaGetLastError());
         *launches += 1;
-        for (int J = 1; J < nblk; ++J) {
-            offdiag_kernel<<<dim3(J, 4), 256, 0, s>>>(L_dev, n, n_pad, J, dense_tmp);
+        if (nblk > 1) {
+            offdiag_kernel<<<dim3(nblk - 1, 4), 256, 0, s>>>(L_dev, n, n_pad, nblk, dense_tmp);
             GPD_CUDA(cudaGetLastError());
             *launches += 1;
         }

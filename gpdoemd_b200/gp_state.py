@@ -87,6 +87,59 @@ class ExactGP:
         self.posterior = _Posterior(L, alpha)
 
 
+class DeviceExactGP:
+    """Exact GP regression whose inference runs on the B200 (``gpd_gp_build``): covariance matrix,
+    blocked Cholesky with GPy's jitchol retries and alpha are formed in device memory, so neither a host LAPACK
+    factorisation nor an n x n upload happens per (re)training.  Same surface as ``ExactGP`` / GPy's GPRegression as
+    far as the reference reads it (``gp[:]``, ``kern``, ``_predictive_variable``, ``posterior``); ``posterior`` is
+    downloaded lazily (one extra device build) because the hot path never needs it on the host."""
+    built_on_device = True
+
+    def __init__(self, Z, Y, kern, noise_var=1.0, device=0):
+        self.X = np.ascontiguousarray(Z, dtype=float)
+        self.Y = np.ascontiguousarray(Y, dtype=float).reshape(len(self.X), 1)
+        self.kern = kern
+        self.noise_var = float(noise_var)
+        self._predictive_variable = self.X
+        self._device = device
+        self._posterior = None
+        self.jitter = None            # jitter the last device factorisation needed (0.0 = none)
+
+    def __getitem__(self, key):
+        assert key == slice(None)
+        return np.r_[self.kern.get_params(), self.noise_var]
+
+    def __setitem__(self, key, v):
+        assert key == slice(None)
+        v = np.asarray(v, dtype=float)
+        k = self.kern.set_params(v)
+        assert k + 1 == len(v), 'hyper-parameter vector has the wrong length'
+        self.noise_var = float(v[k])
+        self._posterior = None
+
+    def _dims(self):
+        dim_p = len(np.asarray(self.kern.kernp.active_dims))
+        return self.X.shape[1] - dim_p, dim_p
+
+    def build(self, ctx, dim_x=None, dim_p=None, want_factor=False):
+        """Run the inference on the device -> gpd_gp* (owned by the caller)."""
+        if dim_x is None:
+            dim_x, dim_p = self._dims()
+        st = GPState.from_gp(self, dim_x, dim_p, with_posterior=False)
+        h, alpha, L, self.jitter = st.build(ctx, self.Y[:, 0], self.noise_var, want_factor=want_factor)
+        if want_factor:
+            self._posterior = _Posterior(np.tril(L), alpha[:, None])
+        return h
+
+    @property
+    def posterior(self):
+        if self._posterior is None:
+            from .context import get_context
+            ctx = get_context(self._device)
+            ctx.lib.gpd_gp_free(self.build(ctx, want_factor=True))
+        return self._posterior
+
+
 class SparseGP(ExactGP):
     """Sparse GP regression with inducing inputs (what GPy's SparseGPRegression / VarDTC computes): the host
     setup behind ``SparseGPModel`` (GPdoemd/models/sparse_gp_model.py:72).  ``gp[:]`` = inducing inputs
@@ -179,7 +232,7 @@ def lower_root_of(W):
 class GPState:
     """Plain-array snapshot of one trained GP in the reference's transformed units."""
 
-    def __init__(self, kernel, dim_x, dim_p, x_active, var_x, ls_x, var_p, ls_p, Z, alpha, L,
+    def __init__(self, kernel, dim_x, dim_p, x_active, var_x, ls_x, var_p, ls_p, Z, alpha=None, L=None,
                  power_x=2.0, power_p=2.0, factor_kind=0):
         self.kernel = kernel
         self.dim_x, self.dim_p = int(dim_x), int(dim_p)
@@ -190,35 +243,40 @@ class GPState:
         self.power_x, self.power_p = float(power_x), float(power_p)
         self.factor_kind = int(factor_kind)   # 0: L = chol(K + noise); 1: L = T with woodbury_inv = T^T T
         self.Z = _lib.as_f64(Z)
-        self.alpha = _lib.as_f64(np.ravel(alpha))
-        self.L = _lib.as_f64(L)
+        self.alpha = None if alpha is None else _lib.as_f64(np.ravel(alpha))
+        self.L = None if L is None else _lib.as_f64(L)
         n = len(self.Z)
         assert self.Z.shape == (n, self.dim_x + self.dim_p)
-        assert self.alpha.shape == (n,) and self.L.shape == (n, n)
+        assert (self.alpha is None) == (self.L is None)
+        assert self.alpha is None or (self.alpha.shape == (n,) and self.L.shape == (n, n))
         assert len(self.ls_x) == len(self.x_active) and len(self.ls_p) == self.dim_p
 
     @classmethod
-    def from_gp(cls, gp, dim_x, dim_p):
+    def from_gp(cls, gp, dim_x, dim_p, with_posterior=True):
         kx, kp = gp.kern.kernx, gp.kern.kernp
         name = kernels.kernel_name_of(kx)
         assert kernels.kernel_name_of(kp) == name, 'both product parts share one class (gp_model.py:60)'
         p_dims = np.asarray(kp.active_dims, dtype=int)
         assert np.array_equal(p_dims, np.arange(dim_x, dim_x + dim_p)), 'kernp acts on columns D..D+P-1'
         sparse = bool(getattr(gp, 'is_sparse', False)) or 'Sparse' in type(gp).__name__
-        if sparse:     # sparse_gp_model.py: posterior lives on the inducing inputs, only woodbury_inv is meaningful
+        if not with_posterior:   # training set + hyper-parameters only: the posterior is formed by gpd_gp_build
+            assert not sparse, 'the device build covers exact GPs'
+            factor, kind, alpha = None, 0, None
+        elif sparse:     # sparse_gp_model.py: posterior lives on the inducing inputs, only woodbury_inv is meaningful
             factor, kind = lower_root_of(np.asarray(gp.posterior.woodbury_inv, dtype=float)), 1
         else:
             factor, kind = np.asarray(gp.posterior.woodbury_chol), 0
+        if with_posterior:
+            alpha = np.asarray(gp.posterior.woodbury_vector)[:, 0]
         return cls(name, dim_x, dim_p, np.asarray(kx.active_dims, dtype=int),
                    float(np.ravel(kx.variance)[0]), np.ravel(kx.lengthscale),
                    float(np.ravel(kp.variance)[0]), np.ravel(kp.lengthscale),
-                   np.asarray(gp._predictive_variable), np.asarray(gp.posterior.woodbury_vector)[:, 0],
+                   np.asarray(gp._predictive_variable), alpha,
                    factor, factor_kind=kind,
                    power_x=float(np.ravel(getattr(kx, 'power', 2.0))[0]),
                    power_p=float(np.ravel(getattr(kp, 'power', 2.0))[0]))
 
-    def upload(self, ctx):
-        """-> opaque device handle (gpd_gp*); the factor is inverted and packed on the device."""
+    def _desc(self):
         d = _lib.GpDesc()
         d.kernel = _lib.KERNEL_IDS[self.kernel]
         d.n = len(self.Z)
@@ -229,6 +287,26 @@ class GPState:
         d.var_p, d.ls_p, d.power_p = self.var_p, dptr(self.ls_p), self.power_p
         d.Z, d.alpha, d.L = dptr(self.Z), dptr(self.alpha), dptr(self.L)
         d.factor_kind = self.factor_kind
+        return d
+
+    def upload(self, ctx):
+        """-> opaque device handle (gpd_gp*); the factor is inverted and packed on the device."""
+        assert self.alpha is not None, 'no posterior: use build()'
+        d = self._desc()
         h = C.c_void_p()
         check(ctx.lib.gpd_gp_upload(ctx.handle, C.byref(d), C.byref(h)))
         return h
+
+    def build(self, ctx, y, noise_var, want_factor=False):
+        """Exact-GP inference on the device (gpd_gp_build) -> (gpd_gp*, alpha, L or None, jitter)."""
+        d = self._desc()
+        n = len(self.Z)
+        y = _lib.as_f64(np.ravel(y))
+        assert y.shape == (n,)
+        alpha = np.empty(n)
+        L = np.empty((n, n)) if want_factor else None
+        jit = C.c_double(0.0)
+        h = C.c_void_p()
+        check(ctx.lib.gpd_gp_build(ctx.handle, C.byref(d), dptr(y), float(noise_var), C.byref(h), dptr(alpha), dptr(L),
+                                   C.byref(jit)))
+        return h, alpha, L, jit.value

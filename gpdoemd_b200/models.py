@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib, kernels
 from ._lib import check, dptr
 from .context import get_context
-from .gp_state import ExactGP, GPState, ProductKernel, SparseGP
+from .gp_state import DeviceExactGP, ExactGP, GPState, ProductKernel, SparseGP
 
 
 class BoxTransform:
@@ -69,7 +69,10 @@ def binary_dimensions(Z, binary_variables):
 
 
 class GPModel:
-    def __init__(self, model_dict, device=0):
+    def __init__(self, model_dict, device=0, build_on_device=False):
+        # build_on_device: gp_surrogate / gp_load_hyp run the exact-GP inference (K, Cholesky, alpha) on the GPU
+        # (gpd_gp_build) instead of host LAPACK + an n x n factor upload per GP
+        self.build_on_device = bool(build_on_device)
         self.name = model_dict.get('name', 'model')
         self.call = model_dict.get('call', None)
         self.dim_x = model_dict['dim_x']
@@ -367,7 +370,11 @@ class GPModel:
                 dim = self.dim_x + self.dim_p
                 kernx = host_cls(self.dim_x - self.dim_b, self.non_binary_variables, 'kernx')
                 kernp = host_cls(self.dim_p, range(self.dim_x, dim), 'kernp')
-                gps[e].append(ExactGP(self.Z[Jr], self.Y[np.ix_(Jr, [e])], ProductKernel(kernx, kernp)))
+                if self.build_on_device:
+                    gps[e].append(DeviceExactGP(self.Z[Jr], self.Y[np.ix_(Jr, [e])], ProductKernel(kernx, kernp),
+                                                device=self._device))
+                else:
+                    gps[e].append(ExactGP(self.Z[Jr], self.Y[np.ix_(Jr, [e])], ProductKernel(kernx, kernp)))
         self.gps = gps
 
     def gp_load_hyp(self, index=None):
@@ -445,7 +452,10 @@ class GPModel:
                 if gp is None:
                     handles[e * R + r] = None
                     continue
-                h = GPState.from_gp(gp, self.dim_x, self.dim_p).upload(ctx)
+                if getattr(gp, 'built_on_device', False):
+                    h = gp.build(ctx, self.dim_x, self.dim_p)
+                else:
+                    h = GPState.from_gp(gp, self.dim_x, self.dim_p).upload(ctx)
                 self._dev_gps.append(h)
                 handles[e * R + r] = h
         bv = np.asarray(self.binary_variables, dtype=np.int32)
@@ -609,8 +619,8 @@ class SparseGPModel(GPModel):
     computation as an exact one with the inducing inputs as "training rows", ``woodbury_vector`` as alpha and a
     triangular root T of ``woodbury_inv`` in place of L^-1 (``GPD_FACTOR_ROOT``)."""
 
-    def __init__(self, model_dict, device=0):
-        super().__init__(model_dict, device=device)
+    def __init__(self, model_dict, device=0, build_on_device=False):
+        super().__init__(model_dict, device=device, build_on_device=False)   # sparse inference stays on the host
         self.max_num_inducing = model_dict.get('max_num_inducing', 500)
 
     def gp_surrogate(self, Z=None, Y=None, kern_x=None, kern_p=None, num_inducing=None):

@@ -105,6 +105,14 @@ int  gpd_flush_l2(gpd_ctx* ctx);
 
 /* ---- GP state hand-off (replaces nothing: training stays on GPy, gp_model.py:96-181) ------- */
 int  gpd_gp_upload(gpd_ctx* ctx, const gpd_gp_desc* desc, gpd_gp** out);
+/* the exact-GP inference itself on the device (gp_model.py:96-147: GPRegression(Zr, Yr, kernx*kernp) in
+ * gp_surrogate, re-run by gp_load_hyp's `gp[:] = hyp`): Ky = K(Z,Z) + (noise_var + 1e-8) I, L = jitchol(Ky)
+ * (blocked FP64 Cholesky; on a non-positive pivot up to 5 retries with jitter mean(diag) * 1e-6 * 10^k like GPy),
+ * alpha = Ky^-1 Y.  desc->alpha and desc->L are ignored; factor_kind must be GPD_FACTOR_CHOL.  Y has n entries
+ * (standardised targets of this output).  alpha_out (n), L_out (n*n, row-major; only the lower triangle is
+ * meaningful) and jitter_out may be NULL: they expose gp.posterior.woodbury_vector / woodbury_chol to the host. */
+int  gpd_gp_build(gpd_ctx* ctx, const gpd_gp_desc* desc, const double* Y, double noise_var, gpd_gp** out,
+                  double* alpha_out, double* L_out, double* jitter_out);
 void gpd_gp_free(gpd_gp* gp);
 
 /* ---- model = GPModel after gp_surrogate/gp_load_hyp (gp_model.py:96-143) ------------------- */
