@@ -5,7 +5,7 @@ FP64 CUDA for sm_100a behind the reference's Python classes and function signatu
 package does not need a GPU; the first call that computes anything does, and raises if the CUDA library
 or device is missing (there is no CPU fallback).
 """
-from . import design_criteria, kernels, marginal, scoring, synthetic
+from . import design_criteria, discrimination_criteria, kernels, marginal, scoring, synthetic
 from .context import Context, get_context
 from .design_criteria import AW, BF, BH, HR, JR
 from .gp_state import DeviceExactGP, ExactGP, GPState, SparseGP
@@ -14,6 +14,6 @@ from .models import GPModel, SparseGPModel
 from .param_covar import laplace_approximation
 from .scoring import ShardedScorer, score_designs, score_designs_dev, score_designs_multi
 
-__all__ = ['GPModel', 'SparseGPModel', 'GPState', 'ExactGP', 'DeviceExactGP', 'SparseGP', 'Context', 'get_context', 'kernels', 'marginal', 'design_criteria',
+__all__ = ['GPModel', 'SparseGPModel', 'GPState', 'ExactGP', 'DeviceExactGP', 'SparseGP', 'Context', 'get_context', 'kernels', 'marginal', 'design_criteria', 'discrimination_criteria',
            'scoring', 'taylor_first_order', 'taylor_second_order', 'laplace_approximation', 'HR', 'BH', 'BF', 'AW', 'JR', 'score_designs',
            'score_designs_dev', 'score_designs_multi', 'ShardedScorer', 'synthetic']

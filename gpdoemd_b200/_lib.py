@@ -65,6 +65,8 @@ _SIGNATURES = {
     'gpd_marginal_assemble': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int32] + [c_double_p] * 7),
     'gpd_criterion': (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, C.c_int64, C.c_int32, C.c_int32,
                                 c_double_p, c_double_p, c_double_p]),
+    'gpd_gauss_loglik': (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, C.c_int64, C.c_int32, C.c_int32,
+                                   c_double_p, c_double_p]),
     'gpd_argmax': (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_double_p, C.POINTER(C.c_int64)]),
     'gpd_score': (C.c_int, [C.c_void_p, c_void_pp, C.c_int32, c_double_p, C.c_int64, C.c_int, C.c_int, c_double_p,
                             c_double_p, c_double_p, c_double_p, C.POINTER(C.c_int64), C.c_int64]),

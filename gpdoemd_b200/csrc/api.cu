@@ -97,6 +97,7 @@ struct gpd_model {
 namespace gpd {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+constexpr double kRbfCoordScaleHost = 0.70710678118654752440;   // == kRbfCoordScale of eval_impl.cuh
 
 struct Span {
     gpd_ctx* c;
@@ -791,7 +792,11 @@ static int gp_create_common(gpd_ctx* c, const gpd_gp_desc* d, gpd_gp** out) {
     const int npair = P * (P + 1) / 2;
     std::vector<double> Xs((size_t)n_pad * nx, 0.0), Zp((size_t)n * P);
     for (int i = 0; i < n; ++i) {
-        for (int k = 0; k < nx; ++k) Xs[(size_t)i * nx + k] = d->Z[(size_t)i * dz + d->x_active[k]] / d->ls_x[k];
+        for (int k = 0; k < nx; ++k) {
+            double v = d->Z[(size_t)i * dz + d->x_active[k]] / d->ls_x[k];
+            if (d->kernel == GPD_KERN_RBF) v *= kRbfCoordScaleHost;      // see eval_impl.cuh: exp(-r^2/2) without the 1/2
+            Xs[(size_t)i * nx + k] = v;
+        }
         for (int a = 0; a < P; ++a) Zp[(size_t)i * P + a] = d->Z[(size_t)i * dz + g->D + a];
     }
     cudaStream_t s = c->stream;
@@ -1315,6 +1320,41 @@ int gpd_criterion(gpd_ctx* c, int kind, const double* mu, const double* S, int64
             GPD_TRY(launch_criterion(s, kind, d_mu, d_S, nc, M, E, d_noise, d_pps, d_dc, d_work));
         }
         GPD_CUDA(cudaMemcpyAsync(dc_out + start, d_dc, sizeof(double) * nc, cudaMemcpyDeviceToHost, s));
+        GPD_CUDA(cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
+int gpd_gauss_loglik(gpd_ctx* c, const double* Y, const double* M, const double* S, int64_t n, int32_t N, int32_t E,
+                     double* logpdf_out, double* maha_out) {
+    GPD_CHECK(c && (n == 0 || (Y && M && S && logpdf_out && maha_out)), "null argument");
+    GPD_CHECK(n >= 0 && N >= 1 && N <= 4096, "bad shape");
+    GPD_CHECK(E >= 1 && E <= kMaxE, "discrimination criteria support 1 <= E <= 8 outputs");
+    GPD_CUDA(cudaSetDevice(c->device));
+    if (n == 0) return 0;
+    const size_t per = sizeof(double) * ((size_t)E + (size_t)N * (E + (size_t)E * E + 2));
+    int64_t chunk = std::min<int64_t>(n, std::max<int64_t>(1, (int64_t)((c->scratch_limit - (1 << 20)) / per)));
+    GPD_TRY(ensure_scratch(c, per * (size_t)chunk + (1 << 20)));
+    Bump bump(c->scratch.p, c->scratch.cap);
+    double* d_Y = bump.take<double>((size_t)chunk * E);
+    double* d_M = bump.take<double>((size_t)chunk * N * E);
+    double* d_S = bump.take<double>((size_t)chunk * N * E * E);
+    double* d_l = bump.take<double>((size_t)chunk * N);
+    double* d_q = bump.take<double>((size_t)chunk * N);
+    GPD_CHECK(bump.off <= bump.cap, "internal: scratch overflow");
+    cudaStream_t s = c->stream;
+    for (int64_t start = 0; start < n; start += chunk) {
+        const int64_t nc = std::min<int64_t>(chunk, n - start);
+        GPD_CUDA(cudaMemcpyAsync(d_Y, Y + (size_t)start * E, sizeof(double) * (size_t)nc * E, cudaMemcpyHostToDevice, s));
+        GPD_CUDA(cudaMemcpyAsync(d_M, M + (size_t)start * N * E, sizeof(double) * (size_t)nc * N * E, cudaMemcpyHostToDevice, s));
+        GPD_CUDA(cudaMemcpyAsync(d_S, S + (size_t)start * N * E * E, sizeof(double) * (size_t)nc * N * E * E,
+                                 cudaMemcpyHostToDevice, s));
+        {
+            Span sp(c, F_CRIT, 1, 0);
+            GPD_TRY(launch_gauss_loglik(s, d_Y, d_M, d_S, nc, N, E, d_l, d_q));
+        }
+        GPD_CUDA(cudaMemcpyAsync(logpdf_out + (size_t)start * N, d_l, sizeof(double) * (size_t)nc * N, cudaMemcpyDeviceToHost, s));
+        GPD_CUDA(cudaMemcpyAsync(maha_out + (size_t)start * N, d_q, sizeof(double) * (size_t)nc * N, cudaMemcpyDeviceToHost, s));
         GPD_CUDA(cudaStreamSynchronize(s));
     }
     return 0;

@@ -130,6 +130,8 @@ int launch_assemble(cudaStream_t s, int order, int N, int E, int P, double* mu, 
 int launch_criterion(cudaStream_t s, int kind, const double* mu, const double* S, int N, int M, int E,
                      const double* noise_dev, const double* pps_dev, double* dc, double* work);
 size_t criterion_work_doubles(int N, int M, int E);
+int launch_gauss_loglik(cudaStream_t s, const double* Y, const double* Mu, const double* S, long long n, int N, int E,
+                        double* logpdf, double* maha);
 int launch_argmax(cudaStream_t s, const double* dc, long long N, long long idx_base, double* best_val_dev,
                   long long* best_idx_dev, int first, void* partial_dev);
 size_t argmax_partial_bytes();

@@ -17,29 +17,34 @@
 
 namespace gpd {
 
-// exp(t) for t <= 0, ~1e-16 relative: t = (m/64) ln2 + u, |u| <= ln2/128;  e^t = 2^(m>>6) * 2^((m&63)/64) * e^u
-// with a degree-5 Taylor polynomial for e^u (|error| < 4e-17) and a 64-entry table.  10 FP64 instructions
-// instead of the ~17 FP64 + ~10 integer instructions of the library exp().
-__device__ __forceinline__ double exp_neg_fast(double t, const double* __restrict__ tab) {
-    const double kMagic = 6755399441055744.0;          // 1.5 * 2^52: the FMA rounds t*64/ln2 to an integer
-    const double z = fma(t, 92.33248261689366, kMagic);
+// exp(-s) for s >= 0, ~1e-16 relative: -s = (m/256) ln2 + u, |u| <= ln2/512;  e^-s = 2^(m>>8) * 2^((m&255)/256) * e^u
+// with a degree-4 Taylor polynomial for e^u (truncation < 4e-17) and a 256-entry table.  9 FP64 instructions
+// (the library exp() needs ~17 FP64 + ~10 integer ones); the underflow guard is an integer compare on the high
+// word of s, which keeps the FP64 pipe free (s >= 700 or +inf -> 0, NaN propagates).
+__device__ __forceinline__ double exp_neg_fast(double s, const double* __restrict__ tab) {
+    const double kMagic = 6755399441055744.0;          // 1.5 * 2^52: the FMA rounds -s*256/ln2 to an integer
+    const double z = fma(s, -369.3299304675746, kMagic);
     const int m = __double2loint(z);
     const double zr = z - kMagic;
-    double u = fma(zr, -0.01083042469326756, t);       // ln2/64 high part (m * hi is exact)
-    u = fma(zr, -2.9815858269852933e-12, u);           // low part
-    double p = fma(u, 1.0 / 120.0, 1.0 / 24.0);
-    p = fma(p, u, 1.0 / 6.0);
+    double u = fma(zr, -0.00270760617331689, -s);      // ln2/256 high part (32 significant bits: m * hi is exact)
+    u = fma(zr, -7.453964567463233e-13, u);            // low part
+    double p = fma(u, 1.0 / 24.0, 1.0 / 6.0);
     p = fma(p, u, 0.5);
     p = fma(p, u, 1.0);
     p = fma(p, u, 1.0);
-    const double r = tab[m & 63] * p;
-    const double s = __hiloint2double(__double2hiint(r) + ((m >> 6) << 20), __double2loint(r));
-    return t < -700.0 ? 0.0 : s;
+    const double r = tab[m & (kExpTabSize - 1)] * p;
+    const double v = __hiloint2double(__double2hiint(r) + ((m >> kExpTabBits) << 20), __double2loint(r));
+    const unsigned hs = (unsigned)__double2hiint(s);
+    return (hs - 0x4085E000u <= 0x7FF00000u - 0x4085E000u) ? 0.0 : v;
 }
+
+// The RBF profile exp(-r^2/2) is evaluated on coordinates pre-scaled by sqrt(1/2) (training rows at upload,
+// candidates when they are loaded), so the kernel loop has no multiply by -0.5.
+constexpr double kRbfCoordScale = 0.70710678118654752440;
 
 template <int KERN>
 __device__ __forceinline__ double kappa_of_r2(double r2, double power, const double* __restrict__ tab) {
-    if (KERN == 0) return exp_neg_fast(-0.5 * r2, tab);          // RBF: exp(-r^2/2)
+    if (KERN == 0) return exp_neg_fast(r2, tab);                 // RBF: exp(-r^2/2), r2 already halved
     double r = sqrt(r2);
     if (KERN == 1) return exp(-r);                               // Exponential
     if (KERN == 2) {                                             // Matern32
@@ -70,7 +75,7 @@ struct EvalSmem {
     static constexpr int kG = (MODE == 0) ? kRows * (kMaxP + 1) : 0;
     static constexpr int kRed = (RG > 1) ? kBlk * NCB : 0;
     static constexpr int kMain = kRec + kG;
-    static constexpr int kDoubles = (kMain > kRed ? kMain : kRed) + 64;
+    static constexpr int kDoubles = (kMain > kRed ? kMain : kRed) + kExpTabSize;
 };
 
 template <int KERN, int NXB, int NCB, int CPT, int RG, int MODE, bool ONE_RHS>
@@ -88,7 +93,7 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
     double* sRec = smem;
     double* sG = smem + SM::kRec;
     double* sRed = smem;                                         // reused after the main loop
-    double* sTab = smem + (SM::kDoubles - 64);
+    double* sTab = smem + (SM::kDoubles - kExpTabSize);
 
     const Item it = items[blockIdx.x];
     const GpView& g = gps[it.gp];
@@ -99,7 +104,8 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
     const int rg = tid / TPG, s = tid % TPG;
     const int n_pad = g.n_pad, nx = g.nx;
     const double power = g.power_x;
-    if (KERN == 0 && tid < 64) sTab[tid] = kExp2Tab[tid];
+    if (KERN == 0)
+        for (int k = tid; k < kExpTabSize; k += kEvalThreads) sTab[k] = kExp2Tab[k];
 
     double xs[CPT][NXB];
 #pragma unroll
@@ -113,6 +119,7 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
             if (d < nx && valid) {
                 const double x = X[(size_t)cand * ldx + g.x_active[d]];
                 v = ((x - g.xmin[d]) / g.xdiff[d]) / g.ls[d];   // trans_x, then GPy's X / lengthscale
+                if (KERN == 0) v *= kRbfCoordScale;
             }
             xs[j][d] = v;
         }
@@ -152,14 +159,29 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
         for (int ii = rg; ii < kEvalRows; ii += RG) {
             const double* __restrict__ rec = sRec + ii * RS;
             double xr[NXB], cr[NCB];
+            if (NXB % 2 == 0) {
 #pragma unroll
-            for (int d = 0; d < NXB; d += 2) {
-                const double2 v = *reinterpret_cast<const double2*>(rec + d);
-                xr[d] = v.x;
-                xr[d + 1] = v.y;
+                for (int d = 0; d < NXB; d += 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(rec + d);
+                    xr[d] = v.x;
+                    xr[d + 1] = v.y;
+                }
+#pragma unroll
+                for (int c = 0; c < NCB; ++c) cr[c] = rec[NXB + c];
+            } else {
+                // odd NXB: the record [x | C columns] is read as RS/2 16-byte vectors
+                double rv[RS];
+#pragma unroll
+                for (int d = 0; d < RS; d += 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(rec + d);
+                    rv[d] = v.x;
+                    rv[d + 1] = v.y;
+                }
+#pragma unroll
+                for (int d = 0; d < NXB; ++d) xr[d] = rv[d];
+#pragma unroll
+                for (int c = 0; c < NCB; ++c) cr[c] = rv[NXB + c];
             }
-#pragma unroll
-            for (int c = 0; c < NCB; ++c) cr[c] = rec[NXB + c];
             const int row = i0 + ii;
             const int sw = (row & 3) << 2;
             double kap[CPT];
@@ -249,7 +271,7 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
     }
 }
 
-// ---- bucket dispatch: NXB in {2,4,8}; MODE 0 column buckets {2,5,8,11,17,28,72}; MODE 1 {3,10,28,55} ----
+// ---- bucket dispatch: NXB in {2,3,4,8}; MODE 0 column buckets {2,5,8,11,17,28,72}; MODE 1 {3,10,28,55} ----
 template <int KERN, int NXB, int NCB, int CPT, int RG, int MODE>
 static int launch_one(cudaStream_t s, int nitems, int ncols, const GpView* gps, const Item* items, const double* X,
                       int ldx, int chunk_n, int nrhs, double* panels, const double* beta, const RawOut* raws,
@@ -303,6 +325,7 @@ static int dispatch_nx(cudaStream_t s, int mode, int nitems, int ncols, int nx, 
                        const double* X, int ldx, int chunk_n, int nrhs, double* panels, const double* beta,
                        const RawOut* raws, int ldraw) {
     if (nx <= 2) return dispatch_cols<KERN, 2>(s, mode, nitems, ncols, gps, items, X, ldx, chunk_n, nrhs, panels, beta, raws, ldraw);
+    if (nx == 3) return dispatch_cols<KERN, 3>(s, mode, nitems, ncols, gps, items, X, ldx, chunk_n, nrhs, panels, beta, raws, ldraw);
     if (nx <= 4) return dispatch_cols<KERN, 4>(s, mode, nitems, ncols, gps, items, X, ldx, chunk_n, nrhs, panels, beta, raws, ldraw);
     if (nx <= 8) return dispatch_cols<KERN, 8>(s, mode, nitems, ncols, gps, items, X, ldx, chunk_n, nrhs, panels, beta, raws, ldraw);
     set_error("x-kernel acts on 1..8 non-binary design dimensions");

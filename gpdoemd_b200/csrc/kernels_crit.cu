@@ -446,6 +446,55 @@ int launch_criterion(cudaStream_t s, int kind, const double* mu, const double* S
 }
 
 // ---------------------------------------------------------------------------------------------
+// Gaussian log-density of observations under every rival model's marginal prediction
+// (GPdoemd/discrimination_criteria.py:32-124: gaussian_posterior, gaussian_posterior_update, chi2, akaike all
+// reduce to  log N(y_j; m_ji, S_ji)  and the squared Mahalanobis distance per (observation j, model i))
+// ---------------------------------------------------------------------------------------------
+template <int E>
+__global__ void __launch_bounds__(128) gauss_loglik_kernel(const double* __restrict__ Y, const double* __restrict__ Mu,
+                                                           const double* __restrict__ S, long long n, int N,
+                                                           double* __restrict__ logpdf, double* __restrict__ maha) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n * N) return;
+    const long long j = tid / N;
+    double A[E][E], d[E];
+#pragma unroll
+    for (int a = 0; a < E; ++a) {
+        d[a] = Y[j * E + a] - Mu[tid * E + a];
+#pragma unroll
+        for (int b = 0; b < E; ++b) A[a][b] = S[(tid * E + a) * E + b];
+    }
+    const double det = inv_inplace<E>(A);
+    double q = 0.0;
+#pragma unroll
+    for (int a = 0; a < E; ++a) {
+        double t = 0.0;
+#pragma unroll
+        for (int b = 0; b < E; ++b) t = fma(A[a][b], d[b], t);
+        q = fma(d[a], t, q);
+    }
+    maha[tid] = q;
+    logpdf[tid] = -0.5 * (E * 1.8378770664093453 + log(det) + q);      // log(2 pi)
+}
+
+int launch_gauss_loglik(cudaStream_t s, const double* Y, const double* Mu, const double* S, long long n, int N, int E,
+                        double* logpdf, double* maha) {
+    const long long total = n * N;
+    const unsigned blocks = (unsigned)((total + 127) / 128);
+    switch (E) {
+#define GPD_LL_CASE(EV) \
+    case EV: gauss_loglik_kernel<EV><<<blocks, 128, 0, s>>>(Y, Mu, S, n, N, logpdf, maha); break;
+        GPD_LL_CASE(1) GPD_LL_CASE(2) GPD_LL_CASE(3) GPD_LL_CASE(4) GPD_LL_CASE(5) GPD_LL_CASE(6) GPD_LL_CASE(7) GPD_LL_CASE(8)
+#undef GPD_LL_CASE
+        default:
+            set_error("discrimination criteria support 1 <= E <= 8 outputs");
+            return 3;
+    }
+    GPD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // argmax with numpy semantics, two stages, running (value, index) pair kept on the device
 // ---------------------------------------------------------------------------------------------
 struct Best { double v; long long i; };

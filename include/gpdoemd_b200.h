@@ -171,6 +171,14 @@ int  gpd_marginal_assemble(gpd_ctx* ctx, int order, int64_t N, int32_t E, int32_
  * inputs are never modified (the reference's BH/BF add noise into the caller's s2, :81,:114) */
 int  gpd_criterion(gpd_ctx* ctx, int kind, const double* mu, const double* S, int64_t N,
                    int32_t M, int32_t E, const double* noise, const double* pps, double* dc_out);
+/* ---- discrimination criteria on the observed set (discrimination_criteria.py:32-124) -----------
+ * gaussian_posterior (:32-52), gaussian_posterior_update (:57-66), chi2 (:72-103) and akaike (:109-130) all reduce
+ * to the Gaussian log-density and the squared Mahalanobis distance of every observation j under every model i:
+ *   logpdf_out[j,i] = log N(Y[j]; M[j,i], S[j,i])   (scipy.stats.multivariate_normal.logpdf, :40,:118)
+ *   maha_out[j,i]   = (M[j,i]-Y[j])^T S[j,i]^-1 (M[j,i]-Y[j])                                   (:93-98)
+ * Y (n,E), M (n,N,E), S (n,N,E,E); the sums over j and the weights are a few host flops (n, N are tiny). */
+int  gpd_gauss_loglik(gpd_ctx* ctx, const double* Y, const double* M, const double* S, int64_t n, int32_t N,
+                      int32_t E, double* logpdf_out /*n,N*/, double* maha_out /*n,N*/);
 /* np.argmax with numpy semantics: first index of the maximum, NaN wins (demos/case_study.py:291) */
 int  gpd_argmax(gpd_ctx* ctx, const double* dc, int64_t N, double* best_val, int64_t* best_idx);
 
