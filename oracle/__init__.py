@@ -20,5 +20,10 @@ Parity status:
 * GP predictive mean / variance / p-derivatives: **parity unpinned against real GPy** (GPy absent
   here and on the GPU box).  Pinned instead by internal consistency: central finite differences of
   the oracle's own mean/variance, extended-precision (80-bit) recomputation, sigma^2 via L vs via
-  K^-1, and interpolation at the training inputs (``tests/test_oracle_gp.py``).
+  K^-1, and interpolation at the training inputs (``tests/test_oracle_gp.py``); and by an INDEPENDENT
+  third-party implementation of the same mathematics: scikit-learn's anisotropic RBF / Matern kernels and
+  exact-GP ``predict`` reproduce the oracle's kernel matrices, means and variances
+  (``tests/test_oracle_vs_sklearn.py``).  GPy-specific conventions remain unverified.
+* discrimination criteria on the observed set (``oracle/discrimination.py``): PINNED against the
+  reference's own module (``tests/golden/obs_golden.npz``).
 """
