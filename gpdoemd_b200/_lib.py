@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libgpdoemd_b200.so')
+LIB_PATH = os.environ.get('GPDOEMD_B200_LIB') or os.path.join(_HERE, 'libgpdoemd_b200.so')   # env: A/B builds
 
 KERNEL_IDS = {'RBF': 0, 'Exponential': 1, 'Matern32': 2, 'Matern52': 3, 'Cosine': 4, 'RatQuad': 5}
 CRITERION_IDS = {'HR': 0, 'BH': 1, 'BF': 2, 'AW': 3, 'JR': 4}

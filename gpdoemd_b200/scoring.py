@@ -83,6 +83,61 @@ def score_designs_dev(models, X_dev, N, order=1, criterion='BH', noise_var=None,
     return int(bi.value), bv.value
 
 
+def refine_designs(models, X_start, criterion='BH', order=1, noise_var=None, pps=None, bounds=None, binary=(),
+                   step=None, iters=25, shrink=0.5, tol=1e-6, scorer=None):
+    """Continuous refinement of the best grid designs: batched compass (pattern) search.
+
+    The reference only evaluates a fixed candidate set and takes ``np.argmax`` (demos/case_study.py:279-293).  Here
+    every start point (e.g. the top-k designs of the grid) is improved by polling the 2 * D axis neighbours at the
+    current step length; ALL polls of ALL start points form one candidate batch per iteration and go through the
+    fused device scorer (``gpd_score``), so one iteration costs one pass of the hot path over K * 2D designs.  A point
+    moves to its best improving neighbour, otherwise its step shrinks.  Derivative-free on purpose: the criterion is
+    evaluated by exactly the kernels the parity tests cover, and the criterion value of every point is monotone
+    non-decreasing.
+
+    X_start (K, D) original units; bounds (2, D) [lo; hi] (default: the models' common training box); ``binary``
+    design columns are held fixed; step (D,) initial step (default 5 % of the box); returns
+    ``(X (K, D), dc (K,), evaluations)`` sorted by decreasing criterion.
+    ``scorer(X) -> dc`` replaces the device scorer (host-logic tests)."""
+    X = np.array(X_start, dtype=float, ndmin=2)
+    K, D = X.shape
+    if bounds is None:
+        lo = np.max([m.xmin for m in models], axis=0)
+        hi = np.min([m.xmax for m in models], axis=0)
+    else:
+        lo, hi = np.asarray(bounds[0], dtype=float), np.asarray(bounds[1], dtype=float)
+    assert lo.shape == (D,) and hi.shape == (D,) and np.all(hi >= lo)
+    free = np.array([d for d in range(D) if d not in set(binary)], dtype=int)
+    assert len(free) > 0, 'no continuous design dimension to refine'
+    h0 = 0.05 * (hi - lo) if step is None else np.broadcast_to(np.asarray(step, dtype=float), (D,))
+    H = np.tile(h0, (K, 1))                       # per-point step lengths
+    if scorer is None:
+        def scorer(Xb):
+            return score_designs(models, Xb, order=order, criterion=criterion, noise_var=noise_var, pps=pps)[2]
+    X = np.clip(X, lo, hi)
+    f = np.array(scorer(X), dtype=float)
+    evals = K
+    dirs = np.concatenate([np.eye(D)[free], -np.eye(D)[free]])          # (2F, D)
+    for _ in range(iters):
+        active = np.any(H[:, free] > tol * np.maximum(hi - lo, 1e-300)[free], axis=1)
+        if not np.any(active):
+            break
+        ia = np.nonzero(active)[0]
+        polls = np.clip(X[ia, None, :] + dirs[None, :, :] * H[ia, None, :], lo, hi)      # (A, 2F, D)
+        fp = np.asarray(scorer(polls.reshape(-1, D)), dtype=float).reshape(len(ia), len(dirs))
+        evals += fp.size
+        fp = np.where(np.isnan(fp), -np.inf, fp)
+        j = np.argmax(fp, axis=1)
+        best = fp[np.arange(len(ia)), j]
+        better = best > f[ia]
+        mv = ia[better]
+        X[mv] = polls[better, j[better]]
+        f[mv] = best[better]
+        H[ia[~better]] *= shrink
+    o = np.argsort(-f, kind='stable')
+    return X[o], f[o], evals
+
+
 def shard_bounds(N, rank, world):
     """Contiguous block [lo, hi) of rank: ceil(N/world) candidates each."""
     per = -(-N // world)
