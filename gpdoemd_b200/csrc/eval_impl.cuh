@@ -70,10 +70,10 @@ __device__ __forceinline__ int eval_col(int s, int j) {
 #ifndef GPD_EVAL_UNROLL
 #define GPD_EVAL_UNROLL 4
 #endif
-// training rows per unrolled loop body of eval_kernel: 4 for the small column buckets (C2: 0.843 -> 0.808 ms against
+// training rows per unrolled loop body of eval_kernel: 4 for the RBF kernel's small column buckets (C2: 0.843 -> 0.808 ms against
 // 2; more independent FP64 chains per warp at 25 % occupancy), 2 where the per-row coefficient registers dominate
-template <int NCB>
-struct EvalUnroll { static constexpr int value = (NCB <= 8) ? GPD_EVAL_UNROLL : 2; };
+template <int KERN, int NCB>
+struct EvalUnroll { static constexpr int value = (KERN == 0 && NCB <= 5) ? GPD_EVAL_UNROLL : 2; };   // others spill at 4
 
 template <int NXB, int NCB, int CPT, int RG, int MODE>
 struct EvalSmem {
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
     constexpr int kEvalRows = SM::kRows;
     constexpr int TPG = kBlk / CPT;                              // threads per row group (each covers the 128 candidates)
     constexpr int kEvalThreads = RG * TPG;
-    constexpr int kEvalUnroll = EvalUnroll<NCB>::value;
+    constexpr int kEvalUnroll = EvalUnroll<KERN, NCB>::value;
     __shared__ __align__(16) double smem[SM::kDoubles];
     double* sRec = smem;
     double* sG = smem + SM::kRec;
