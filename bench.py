@@ -16,6 +16,11 @@ import sys
 import threading
 import time
 
+if '--impl' in sys.argv and 'reference' in sys.argv:
+    # the reference arm runs on rank 0 alone and may use every host core; torchrun presets OMP_NUM_THREADS=1
+    for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[_v] = str(os.cpu_count())
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -112,6 +117,16 @@ def cpu_reference_run(cfg, seed, n_sample, steps, warmup):
     return n_sample * steps / dt, dt / steps
 
 
+def blas_threads():
+    """threads NumPy's BLAS/LAPACK actually uses (the `cores` of cpu_baseline)"""
+    try:
+        from threadpoolctl import threadpool_info
+        n = [p.get('num_threads', 1) for p in threadpool_info() if p.get('user_api') in ('blas', 'openmp')]
+        return max(n) if n else (os.cpu_count() or 1)
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_sample_size(cfg):
     # ~10-30 s of CPU work per run: the oracle does ~700 designs/s on C2 (8 cores) and far less on n=4000
     per = {'C2': 4000, 'C3': 48, 'C4': 64, 'C5': 256, 'S2': 4000}
@@ -163,7 +178,7 @@ def main():
         line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
                 'warmup': warm, 'ms_per_step': sps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': config,
-                'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+                'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': blas_threads(), 'kind': 'port',
                                  'sample': '%d candidates per step of the same workload (all models, all criteria)' % ns},
                 'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
         emit(line)
@@ -176,6 +191,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    g.set_default_device(local_rank)
     ctx = g.get_context(local_rank)
     if args.tri_variant is not None:
         ctx.set_option('tri_variant', args.tri_variant)
@@ -283,7 +299,9 @@ def main():
     best = {c: (res[c][1], res[c][0]) for c in crits}
     if dist is not None:
         sc = g.ShardedScorer()
-        t = torch.tensor([t_ms, e2e_ms if e2e_ms is not None else 0.0], dtype=torch.float64, device='cuda')
+        torch.cuda.set_device(local_rank)     # the library and torch share the CUDA runtime's current device
+        t = torch.tensor([t_ms, e2e_ms if e2e_ms is not None else 0.0], dtype=torch.float64,
+                         device=torch.device('cuda', local_rank))
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_ms, e2e_max = float(t[0]), float(t[1])
         e2e_ms = e2e_max if e2e_ms is not None else None
@@ -335,7 +353,7 @@ def main():
     if not args.no_cpu_baseline and world >= 1:
         ns = cpu_sample_size(cfg)[args.config]
         v, sps = cpu_reference_run(cfg, seed, ns, 1, 0)
-        line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+        line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': blas_threads(), 'kind': 'port',
                                 'sample': '%d candidates of the same workload, 1 step, NumPy/LAPACK threads = all cores' % ns}
     emit(line)
     if dist is not None:

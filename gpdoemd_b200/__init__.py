@@ -6,7 +6,7 @@ package does not need a GPU; the first call that computes anything does, and rai
 or device is missing (there is no CPU fallback).
 """
 from . import design_criteria, discrimination_criteria, kernels, marginal, scoring, synthetic
-from .context import Context, get_context
+from .context import Context, get_context, set_default_device
 from .design_criteria import AW, BF, BH, HR, JR
 from .gp_state import DeviceExactGP, ExactGP, GPState, SparseGP
 from .marginal import taylor_first_order, taylor_second_order
@@ -14,6 +14,6 @@ from .models import GPModel, SparseGPModel
 from .param_covar import laplace_approximation
 from .scoring import ShardedScorer, refine_designs, score_designs, score_designs_dev, score_designs_multi
 
-__all__ = ['GPModel', 'SparseGPModel', 'GPState', 'ExactGP', 'DeviceExactGP', 'SparseGP', 'Context', 'get_context', 'kernels', 'marginal', 'design_criteria', 'discrimination_criteria',
+__all__ = ['GPModel', 'SparseGPModel', 'GPState', 'ExactGP', 'DeviceExactGP', 'SparseGP', 'Context', 'get_context', 'set_default_device', 'kernels', 'marginal', 'design_criteria', 'discrimination_criteria',
            'scoring', 'taylor_first_order', 'taylor_second_order', 'laplace_approximation', 'HR', 'BH', 'BF', 'AW', 'JR', 'score_designs',
            'score_designs_dev', 'score_designs_multi', 'refine_designs', 'ShardedScorer', 'synthetic']

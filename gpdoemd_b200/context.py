@@ -104,8 +104,27 @@ class Context:
         return v.value, int(i.value)
 
 
-def get_context(device=0):
+_default_device = None
+
+
+def set_default_device(device):
+    """Device used by the entry points that take no model (design / discrimination criteria, marginal assembly)."""
+    global _default_device
+    _default_device = int(device)
+
+
+def default_device():
+    """set_default_device() value, else LOCAL_RANK (one process per GPU under torchrun), else 0."""
+    if _default_device is not None:
+        return _default_device
+    import os
+    return int(os.environ.get('LOCAL_RANK', 0))
+
+
+def get_context(device=None):
     """Process-wide context of a device (created on first use; raises if there is no B200)."""
+    if device is None:
+        device = default_device()
     ctx = _contexts.get(int(device))
     if ctx is None:
         ctx = Context(device)

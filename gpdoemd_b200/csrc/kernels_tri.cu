@@ -73,7 +73,10 @@ __device__ __forceinline__ void consumer_bar(int nthreads) {
 //   CPS 1: 4 stages x (16 KiB A + 16 KiB B)      CPS 2: 3 stages x (32 KiB A + 32 KiB B)
 template <int CPS>
 struct TriCfg {
-    static constexpr int kStages = (CPS == 1) ? 4 : 3;
+#ifndef GPD_TRI_STAGES1
+#define GPD_TRI_STAGES1 4
+#endif
+    static constexpr int kStages = (CPS == 1) ? GPD_TRI_STAGES1 : 3;
     static constexpr int kStageElems = kChunkElems * CPS;
     static constexpr uint32_t kStageBytes = kStageElems * sizeof(double);
 };

@@ -40,7 +40,7 @@ def _reshape(mu, s2, noise_var=None, pps=None):
     return mu, s2, noise_var, pps, n, M, E
 
 
-def _run(kind, mu, s2, noise_var, pps, device=0):
+def _run(kind, mu, s2, noise_var, pps, device=None):
     mu, s2v, noise_var, pps, n, M, E = _reshape(mu, s2, noise_var, pps)
     dc = np.empty(n)
     ctx = get_context(device)

@@ -14,7 +14,7 @@ from ._lib import check, dptr
 from .context import get_context
 
 
-def _loglik(Y, M, S, device=0):
+def _loglik(Y, M, S, device=None):
     """-> logpdf (n, N), maha (n, N) for Y (n, E), M (n, N, E), S (n, N, E, E)."""
     Y, M, S = _lib.as_f64(Y), _lib.as_f64(M), _lib.as_f64(S)
     n, N, E = M.shape

@@ -32,7 +32,7 @@ def _device_marginal(model, xnew, order):
     return M, S
 
 
-def _assemble(model, xnew, order, device=0):
+def _assemble(model, xnew, order, device=None):
     N, E, D = len(xnew), model.num_outputs, model.dim_p
     M, s2 = model.predict(xnew)
     M, s2 = _lib.as_f64(M).copy(), _lib.as_f64(s2)

@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import check, dptr
-from .context import get_context
+from .context import default_device, get_context
 from .design_criteria import _reshape
 
 
@@ -183,7 +183,8 @@ class ShardedScorer:
         import torch
         dist = self.dist
         backend = dist.get_backend(self.group)
-        dev = device if device is not None else ('cuda' if backend == 'nccl' else 'cpu')
+        # the rank's own GPU, not "current device": the library and torch share the CUDA runtime's current device
+        dev = device if device is not None else ('cuda:%d' % default_device() if backend == 'nccl' else 'cpu')
         v = torch.tensor([best_val], dtype=torch.float64, device=dev)
         i = torch.tensor([best_idx], dtype=torch.int64, device=dev)
         vs = [torch.empty_like(v) for _ in range(self.world)]
