@@ -139,3 +139,16 @@ def test_from_reference_adopts_everything():
     for k in ('xmin', 'xmax', 'pmin', 'pmax', 'ymean', 'ystd', 'pmean', 'Sigma'):
         assert np.array_equal(getattr(m, k), getattr(om, k)), k
     assert m.gps is om.gps and m.hyp is om.hyp
+
+
+def test_default_device_follows_local_rank(monkeypatch):
+    """Entry points without a model argument (criteria, assembly) must run on the rank's own GPU under torchrun:
+    the library and torch share the CUDA runtime's current device (an 8-GPU bench once moved every rank to cuda:0)."""
+    from gpdoemd_b200 import context
+    monkeypatch.setattr(context, '_default_device', None)
+    monkeypatch.delenv('LOCAL_RANK', raising=False)
+    assert context.default_device() == 0
+    monkeypatch.setenv('LOCAL_RANK', '5')
+    assert context.default_device() == 5
+    context.set_default_device(3)
+    assert context.default_device() == 3
