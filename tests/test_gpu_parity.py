@@ -367,3 +367,45 @@ def test_laplace_approximation_on_device_model(gpu_ctx):
         gm.Sigma = S1                      # and it feeds straight back into the marginal
         M1, V1 = g.taylor_first_order(gm, Xobs)
         assert np.all(np.isfinite(V1))
+
+
+def test_scoring_plan_cache_is_transparent(gpu_ctx):
+    """The fused scorer reuses the previous call's plan and device tables (api.cu: ScoreState).  Every change that
+    could make them stale -- new pmean, another scratch user in between, other N / noise / criteria, rebuilt models --
+    must give the same numbers as a cold call, i.e. as the oracle."""
+    import gpdoemd_b200 as g
+    from gpdoemd_b200 import synthetic
+    oms, ds = helpers.oracle_models(61, M=3, E=2, D=3, P=2, n=140, kernel='Matern52')
+    gms = helpers.gpu_models(oms)
+    lo = np.max([d['xlo'] for d in ds], axis=0)
+    hi = np.min([d['xhi'] for d in ds], axis=0)
+    X = synthetic.candidates(8, 700, 3, lo, hi)
+
+    def oracle_dc(Xc, crit, noise):
+        mu = np.zeros((len(Xc), 3, 2))
+        S = np.zeros((len(Xc), 3, 2, 2))
+        for i, om in enumerate(oms):
+            mu[:, i], S[:, i] = omarg.taylor_first_order(om, Xc)
+        return ocrit.CRITERIA[crit](mu, S, noise, None)
+
+    def check(Xc, crit='BH', noise=0.01):
+        bi, bv, dc = g.score_designs(gms, Xc, order=1, criterion=crit, noise_var=noise)
+        d0 = oracle_dc(Xc, crit, noise)
+        assert helpers.relerr(dc, d0, np.abs(d0).mean()) < TOL_CRIT and bi == int(np.argmax(d0))
+        return dc
+    a = check(X)
+    b = check(X)                                   # warm call: cached plan
+    assert np.array_equal(a, b)
+    for om, gm in zip(oms, gms):                   # new parameter estimate: tables change in place, plan stays
+        p = om.pmean + 0.05 * (om.pmax - om.pmin)
+        om.pmean = p.copy()
+        gm.pmean = p.copy()
+    c = check(X)
+    assert not np.array_equal(a, c)
+    gms[0].predict(X[:50])                         # another scratch user between two scoring calls
+    assert np.array_equal(check(X), c)
+    check(X[:333])                                 # other N
+    check(X, noise=0.05)                           # other noise
+    check(X, crit='JR')                            # other criterion
+    gms = helpers.gpu_models(oms)                  # rebuilt models (old handles freed)
+    assert np.array_equal(check(X), c)
