@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get('GPDOEMD_B200_LIB') or os.path.join(_HERE, 'libgpdoemd
 
 KERNEL_IDS = {'RBF': 0, 'Exponential': 1, 'Matern32': 2, 'Matern52': 3, 'Cosine': 4, 'RatQuad': 5}
 CRITERION_IDS = {'HR': 0, 'BH': 1, 'BF': 2, 'AW': 3, 'JR': 4}
-FAMILIES = ('eval', 'tri', 'gram', 'marginal', 'criteria', 'argmax', 'setup')
+FAMILIES = ('eval', 'tri', 'gram', 'marginal', 'criteria', 'argmax', 'setup', 'tri_head')
 NFAMILIES = len(FAMILIES)
 
 c_double_p = C.POINTER(C.c_double)

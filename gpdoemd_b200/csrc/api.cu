@@ -43,14 +43,17 @@ struct DevBuf {
     }
 };
 
-enum Family { F_EVAL = 0, F_TRI = 1, F_GRAM = 2, F_MARG = 3, F_CRIT = 4, F_ARGMAX = 5, F_SETUP = 6 };
+enum Family { F_EVAL = 0, F_TRI = 1, F_GRAM = 2, F_MARG = 3, F_CRIT = 4, F_ARGMAX = 5, F_SETUP = 6, F_TRI_HEAD = 7 };
 }  // namespace gpd
 
 using namespace gpd;
 
 struct gpd_ctx {
     int device = 0, num_sms = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;          // high priority: every kernel of the library
+    cudaStream_t stream2 = nullptr;         // low priority: only the evaluation overlapped with a tail wave (run_chunk)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int tail_overlap = 1;                   // option "tail_overlap"
     uint64_t scratch_limit = 6ull << 30;
     DevBuf scratch, tables, flush;
     uint64_t launches = 0;
@@ -110,18 +113,20 @@ struct Span {
     gpd_ctx* c;
     int fam;
     cudaEvent_t a = nullptr, b = nullptr;
-    Span(gpd_ctx* ctx, int family, uint64_t nlaunch, double flops) : c(ctx), fam(family) {
+    cudaStream_t st;
+    Span(gpd_ctx* ctx, int family, uint64_t nlaunch, double flops, cudaStream_t on = nullptr)
+        : c(ctx), fam(family), st(on ? on : ctx->stream) {
         c->launches += nlaunch;
         if (!c->profile) return;
         c->fam_launches[fam] += nlaunch;
         c->fam_flops[fam] += flops;
         a = take();
         b = take();
-        cudaEventRecord(a, c->stream);
+        cudaEventRecord(a, st);
     }
     ~Span() {
         if (!a) return;
-        cudaEventRecord(b, c->stream);
+        cudaEventRecord(b, st);
         c->spans.push_back({a, b, fam});
     }
     cudaEvent_t take() {
@@ -176,6 +181,7 @@ struct Group {          // GPs evaluated by one eval launch: same kernel class, 
     int kernel, nx, P;
     std::vector<int> entries;
     int item_begin = 0, item_count = 0;
+    int head_begin = 0, head_count = 0, big_begin = 0, big_count = 0;   // in Plan::items2_dev (tail overlap)
 };
 struct ModelBufs {
     RawOut raw;
@@ -200,6 +206,8 @@ struct Plan {
     // device tables
     GpView* views_dev = nullptr;
     Item* items_dev = nullptr;
+    Item* items2_dev = nullptr;     // the same items as [head tiles of every GP][remaining tiles of every GP]
+    int head_tiles = 0, n_head = 0, n_big = 0;
     RawOut* raws_dev = nullptr;
     double *panels_in = nullptr, *panels_out = nullptr, *panels_beta = nullptr;
     int nitems = 0;
@@ -405,12 +413,42 @@ static int plan_materialize(gpd_ctx* c, Plan& pl, Bump& bump) {
         grp.item_count = (int)items.size() - grp.item_begin;
     }
     pl.nitems = (int)items.size();
+    // Tail overlap (first-order path): the persistent triangular kernel runs ceil(items / SMs) waves and the last,
+    // partial one leaves most SMs idle for a whole item time (C2: 6256 items = 42.27 waves).  The first `head_tiles`
+    // candidate tiles of every GP are therefore split off such that the REST fills complete waves; the head's
+    // triangular launch (few CTAs) then runs concurrently with the evaluation of the rest on a second stream.
+    std::vector<Item> items2;
+    pl.head_tiles = 0;
+    pl.n_head = pl.n_big = 0;
+    if (c->tail_overlap && !pl.need_W) {
+        const long long S = c->num_sms, G = (long long)pl.entries.size();
+        long long a = S, b = G;
+        while (b) { const long long t = a % b; a = b; b = t; }      // a = gcd(S, G)
+        const long long period = S / a;                              // tiles per GP that make whole waves
+        const long long h = pl.tiles % period;
+        if (h > 0 && (long long)pl.tiles * G > S && h < pl.tiles) pl.head_tiles = (int)h;
+    }
+    if (pl.head_tiles) {
+        for (int pass = 0; pass < 2; ++pass)
+            for (auto& grp : pl.groups) {
+                const int begin = (int)items2.size();
+                for (int ei : grp.entries)
+                    for (int t = pass ? pl.head_tiles : 0; t < (pass ? pl.tiles : pl.head_tiles); ++t) items2.push_back(Item{ei, t});
+                (pass ? grp.big_begin : grp.head_begin) = begin;
+                (pass ? grp.big_count : grp.head_count) = (int)items2.size() - begin;
+            }
+        pl.n_head = (int)pl.entries.size() * pl.head_tiles;
+        pl.n_big = (int)items2.size() - pl.n_head;
+    }
     pl.views_dev = bump.take<GpView>(views.size());
     pl.items_dev = bump.take<Item>(items.size());
+    pl.items2_dev = items2.empty() ? nullptr : bump.take<Item>(items2.size());
     pl.raws_dev = bump.take<RawOut>(M);
     GPD_CHECK(bump.off <= bump.cap, "internal: scratch plan overflow");
     GPD_CUDA(cudaMemcpyAsync(pl.views_dev, views.data(), sizeof(GpView) * views.size(), cudaMemcpyHostToDevice, c->stream));
     GPD_CUDA(cudaMemcpyAsync(pl.items_dev, items.data(), sizeof(Item) * items.size(), cudaMemcpyHostToDevice, c->stream));
+    if (pl.items2_dev)
+        GPD_CUDA(cudaMemcpyAsync(pl.items2_dev, items2.data(), sizeof(Item) * items2.size(), cudaMemcpyHostToDevice, c->stream));
     GPD_CUDA(cudaMemcpyAsync(pl.raws_dev, raws.data(), sizeof(RawOut) * M, cudaMemcpyHostToDevice, c->stream));
     // pageable-source cudaMemcpyAsync returns once the data is staged: the host vectors may go out of scope
     return 0;
@@ -448,20 +486,46 @@ static int run_chunk(gpd_ctx* c, Plan& pl, const double* X_dev, int ldx, int nc)
     // count check (identity routing uses chunk_n = nc).
     (void)tiles_used;
     double n2sum = 0;   // algorithmic flops: n^2 per candidate per right-hand side
-    for (auto& grp : pl.groups) {
-        const int nrhs = pl.need_W ? 1 + grp.P : 1;
-        const int ncols = ncols_for(pl.flags, grp.P);
-        double evflops = 0;
-        for (int ei : grp.entries) {
-            const gpd_gp* g = pl.entries[ei].gp;
-            const double share = 1.0 / pl.models[pl.entries[ei].model]->R;
-            evflops += share * (double)nc * g->n * (3.0 * g->nx + 45.0 + 2.0 * ncols + nrhs);
-            n2sum += share * (double)nc * (double)g->n * g->n * nrhs;
-        }
-        Span sp(c, F_EVAL, 1, evflops);
-        GPD_TRY(launch_eval(s, pl.views_dev, pl.items_dev + grp.item_begin, grp.item_count, X_dev, ldx, nc, nrhs, ncols,
-                            grp.kernel, grp.nx, pl.panels_in, pl.raws_dev, pl.mb[pl.entries[grp.entries[0]].model].ldraw));
+    const bool overlap = pl.head_tiles > 0 && !pl.need_W && nc > pl.head_tiles * kBlk;
+    if (overlap) {
+        GPD_CUDA(cudaEventRecord(c->ev_fork, s));
+        GPD_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
     }
+    for (int pass = 0; pass < (overlap ? 2 : 1); ++pass) {
+        // pass 0: all items (or the head tiles) on the main, high-priority stream; pass 1: the remaining tiles on the
+        // second stream, concurrently with the head's evaluation and triangular launch
+        cudaStream_t es = pass ? c->stream2 : s;
+        for (auto& grp : pl.groups) {
+            const int nrhs = pl.need_W ? 1 + grp.P : 1;
+            const int ncols = ncols_for(pl.flags, grp.P);
+            const Item* its = !overlap ? pl.items_dev + grp.item_begin : pl.items2_dev + (pass ? grp.big_begin : grp.head_begin);
+            const int nits = !overlap ? grp.item_count : (pass ? grp.big_count : grp.head_count);
+            const double part = (double)nits / std::max(1, grp.item_count);
+            double evflops = 0;
+            for (int ei : grp.entries) {
+                const gpd_gp* g = pl.entries[ei].gp;
+                const double share = part / pl.models[pl.entries[ei].model]->R;
+                evflops += share * (double)nc * g->n * (3.0 * g->nx + 45.0 + 2.0 * ncols + nrhs);
+                n2sum += share * (double)nc * (double)g->n * g->n * nrhs;
+            }
+            Span sp(c, F_EVAL, 1, evflops, es);
+            GPD_TRY(launch_eval(es, pl.views_dev, its, nits, X_dev, ldx, nc, nrhs, ncols, grp.kernel, grp.nx, pl.panels_in,
+                                pl.raws_dev, pl.mb[pl.entries[grp.entries[0]].model].ldraw));
+        }
+        if (pass) GPD_CUDA(cudaEventRecord(c->ev_join, c->stream2));
+    }
+    if (overlap) {
+        const double fh = (double)pl.n_head / (pl.n_head + pl.n_big);
+        {
+            Span sp(c, F_TRI_HEAD, 1, n2sum * fh);
+            GPD_TRY(launch_tri(s, pl.views_dev, pl.items2_dev, pl.n_head, 1, 1, 1, 0, pl.panels_in, nullptr, pl.raws_dev,
+                               tri_row_groups(c->tri_variant), nc, c->num_sms, c->tri_variant, tri_cps_for(c, pl), c->tri_trim));
+        }
+        GPD_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
+        Span sp(c, F_TRI, 1, n2sum * (1.0 - fh));
+        GPD_TRY(launch_tri(s, pl.views_dev, pl.items2_dev + pl.n_head, pl.n_big, 1, 1, 1, 0, pl.panels_in, nullptr, pl.raws_dev,
+                           tri_row_groups(c->tri_variant), nc, c->num_sms, c->tri_variant, tri_cps_for(c, pl), c->tri_trim));
+    } else
     if (!pl.need_W) {
         Span sp(c, F_TRI, 1, n2sum);
         GPD_TRY(launch_tri(s, pl.views_dev, pl.items_dev, pl.nitems, 1, 1, 1, 0, pl.panels_in, nullptr, pl.raws_dev,
@@ -542,7 +606,12 @@ int gpd_create(int device, gpd_ctx** out) {
     gpd_ctx* c = new gpd_ctx();
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
-    GPD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    int prio_least = 0, prio_greatest = 0;
+    GPD_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    GPD_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest));
+    GPD_CUDA(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_least));
+    GPD_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    GPD_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     GPD_CUDA(cudaEventCreate(&c->t0));
     GPD_CUDA(cudaEventCreate(&c->t1));
     GPD_CUDA(cudaMalloc(&c->best_val_dev, sizeof(double) * kMaxKinds));
@@ -572,6 +641,9 @@ void gpd_destroy(gpd_ctx* c) {
     cudaFree(c->argmax_partial);
     cudaFreeHost(c->result_pinned);
     delete c->score_state;
+    cudaEventDestroy(c->ev_fork);
+    cudaEventDestroy(c->ev_join);
+    cudaStreamDestroy(c->stream2);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -600,6 +672,11 @@ int gpd_set_option(gpd_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "tri_cps")) {
         GPD_CHECK(value >= 0 && value <= 2, "tri_cps is 0 (automatic), 1 or 2");
         c->tri_cps = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "tail_overlap")) {
+        GPD_CHECK(value == 0 || value == 1, "tail_overlap is 0 or 1");
+        c->tail_overlap = (int)value;
         return 0;
     }
     if (!strcmp(name, "tri_trim")) {
@@ -1149,7 +1226,7 @@ static int hooks_host(gpd_model* mo, const double* X, int64_t N, int flags, cons
     const int D = mo->D, E = mo->E, P = mo->P;
     GPD_TRY(plan_build(c, &mo, 1, flags, N, sizeof(double) * D, 0, pl));
     const size_t total = pl.per_cand_bytes * ((size_t)pl.chunk + kBlk) + (8u << 20) + pl.entries.size() * sizeof(GpView) +
-                         (size_t)pl.entries.size() * pl.tiles * sizeof(Item);
+                         (size_t)pl.entries.size() * pl.tiles * sizeof(Item) * 2;
     GPD_TRY(ensure_scratch(c, total));
     Bump bump(c->scratch.p, c->scratch.cap);
     double* X_dev = bump.take<double>((size_t)pl.chunk * D);
@@ -1239,7 +1316,7 @@ int gpd_marginal(gpd_model* mo, const double* X, int64_t N, int order, double* m
     const size_t extra = sizeof(double) * ((size_t)D + (size_t)E * E + (order == 2 ? (size_t)E * P * P + E : 0));
     GPD_TRY(plan_build(c, &mo, 1, order_flags(order), N, extra, 0, pl));
     const size_t total = pl.per_cand_bytes * ((size_t)pl.chunk + kBlk) + (8u << 20) + pl.entries.size() * sizeof(GpView) +
-                         (size_t)pl.entries.size() * pl.tiles * sizeof(Item);
+                         (size_t)pl.entries.size() * pl.tiles * sizeof(Item) * 2;
     GPD_TRY(ensure_scratch(c, total));
     Bump bump(c->scratch.p, c->scratch.cap);
     double* X_dev = bump.take<double>((size_t)pl.chunk * D);
@@ -1456,7 +1533,7 @@ static int score_impl(gpd_ctx* c, gpd_model* const* models, int32_t M, const dou
         if (order == 2) extra += sizeof(double) * ((size_t)E * maxP * maxP + E);
         GPD_TRY(plan_build(c, models, M, order_flags(order), N, extra, 0, pl));
         const size_t total = pl.per_cand_bytes * ((size_t)pl.chunk + kBlk) + (8u << 20) + pl.entries.size() * sizeof(GpView) +
-                             (size_t)pl.entries.size() * pl.tiles * sizeof(Item);
+                             (size_t)pl.entries.size() * pl.tiles * sizeof(Item) * 2;
         GPD_TRY(ensure_scratch(c, total));
         Bump bump(c->scratch.p, c->scratch.cap);
         const int Nc0 = pl.chunk;

@@ -82,6 +82,8 @@ const char* gpd_last_error(void);
 int  gpd_set_scratch_bytes(gpd_ctx* ctx, uint64_t bytes);
 /* tuning knobs: "tri_variant" 0 = 16 warps (32x32 warp tiles), 1 = 8 warps (64x32);
  * "tri_cps" 0 = automatic, 1 = 4 pipeline stages of 16 k, 2 = 3 stages of 32 k;
+ * "tail_overlap" 1 (default) = first-order path: the candidate tiles that would form the last, partial wave of the
+ *   persistent triangular kernel are evaluated and contracted first, concurrently with the evaluation of the rest;
  * "tri_trim" 1 (default) = the all-padding 8-row blocks (rows n..n_pad) of the last row block are skipped */
 int  gpd_set_option(gpd_ctx* ctx, const char* name, int64_t value);
 /* number of CUDA kernels launched by this context so far (bench.py `gpu_launches`) */
@@ -89,8 +91,9 @@ uint64_t gpd_launch_count(gpd_ctx* ctx);
 /* device-time accounting per kernel family with CUDA events on the library's stream:
  * enable, run, then read the accumulated milliseconds / launch counts.  family index:
  * 0 eval (kernel+derivative rows), 1 tri (DMMA triangular contraction), 2 gram, 3 marginal,
- * 4 criteria, 5 argmax, 6 setup (p-state, routing, packing) */
-enum { GPD_NFAMILIES = 7 };
+ * 4 criteria, 5 argmax, 6 setup (p-state, routing, packing), 7 tri_head (the small triangular launch over the
+ * head tiles that runs concurrently with the evaluation of the remaining tiles, option "tail_overlap") */
+enum { GPD_NFAMILIES = 8 };
 int  gpd_profile_enable(gpd_ctx* ctx, int on);
 int  gpd_profile_read(gpd_ctx* ctx, double ms_out[GPD_NFAMILIES], uint64_t launches_out[GPD_NFAMILIES],
                       double flops_out[GPD_NFAMILIES]);
