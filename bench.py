@@ -142,6 +142,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--candidates', type=float, default=None, help='override N per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-stepwise', action='store_true', help='skip the informational drop-in-functions leg')
     ap.add_argument('--tri-variant', type=int, default=None)
     ap.add_argument('--tri-cps', type=int, default=None)
     ap.add_argument('--tri-trim', type=int, default=None)
@@ -277,7 +278,7 @@ def main():
     # the reference's own call pattern (demos/case_study.py:284-293) through the drop-in functions: one
     # taylor_* call per model (host arrays in and out), then one call per criterion -- informational
     stepwise_ms = None
-    if X_host is not None and N <= 2000000:
+    if X_host is not None and N <= 2000000 and not args.no_stepwise:
         marg = g.taylor_first_order if order == 1 else g.taylor_second_order
         E, Mn = cfg['E'], cfg['M']
 

@@ -409,3 +409,52 @@ def test_scoring_plan_cache_is_transparent(gpu_ctx):
     check(X, crit='JR')                            # other criterion
     gms = helpers.gpu_models(oms)                  # rebuilt models (old handles freed)
     assert np.array_equal(check(X), c)
+
+
+def test_tail_overlap_is_bit_identical_and_matches_the_oracle(gpu_ctx):
+    """The head / rest split of the candidate tiles (two streams, api.cu run_chunk) changes the launch structure only:
+    criterion vectors are bit-identical with the option on and off, and equal to the oracle on a sample."""
+    import gpdoemd_b200 as g
+    from gpdoemd_b200 import synthetic
+    oms, ds = helpers.oracle_models(71, M=2, E=2, D=3, P=2, n=130, kernel='RBF')
+    gms = helpers.gpu_models(oms)
+    lo = np.max([d['xlo'] for d in ds], axis=0)
+    hi = np.min([d['xhi'] for d in ds], axis=0)
+    N = 128 * 163 + 17                               # 164 tiles x 4 GPs: head = 164 mod 37 = 16 tiles, rest = 4 waves
+    X = synthetic.candidates(12, N, 3, lo, hi)
+    out = {}
+    for flag in (1, 0):
+        gpu_ctx.set_option('tail_overlap', flag)
+        out[flag] = g.score_designs_multi(gms, X, ['BH', 'JR'], order=1, noise_var=0.02)
+    gpu_ctx.set_option('tail_overlap', 1)
+    for c in ('BH', 'JR'):
+        assert out[0][c][0] == out[1][c][0] and out[0][c][1] == out[1][c][1]
+        assert np.array_equal(out[0][c][2], out[1][c][2])
+    sel = np.r_[0:150, 128 * 16 - 5:128 * 16 + 150, N - 150:N]       # head, head/rest boundary, tail of the rest
+    mu = np.zeros((len(sel), 2, 2))
+    S = np.zeros((len(sel), 2, 2, 2))
+    for i, om in enumerate(oms):
+        mu[:, i], S[:, i] = omarg.taylor_first_order(om, X[sel])
+    for c in ('BH', 'JR'):
+        d0 = ocrit.CRITERIA[c](mu, S, 0.02, None)
+        assert helpers.relerr(out[1][c][2][sel], d0, np.abs(d0).mean()) < TOL_CRIT
+
+
+@pytest.mark.parametrize('kernel,n', [('Matern52', 4000), ('RBF', 2100)])
+def test_large_training_set_parity(kernel, n, gpu_ctx):
+    """n_train of the C3-C5 configs (n_pad = 4096: 32 row blocks, 96 padding rows trimmed, 4 x 16 k pipeline) and an
+    ill-conditioned RBF factor with a ragged size, on a candidate sample the oracle finishes in seconds."""
+    oms, ds = helpers.oracle_models(91, M=1, E=1, D=3, P=3, n=n, kernel=kernel)
+    gm = helpers.gpu_models(oms)[0]
+    om = oms[0]
+    from gpdoemd_b200 import synthetic
+    X = synthetic.candidates(2, 200, 3, ds[0]['xlo'], ds[0]['xhi'])
+    ystd, vscale = _scales(om)
+    pd = om.pmax - om.pmin
+    M0, S0 = om.predict(X)
+    M1, S1 = gm.predict(X)
+    assert helpers.relerr(M1, M0, ystd) < TOL_MEAN
+    assert helpers.relerr(S1, S0, vscale) < TOL_VAR
+    assert helpers.relerr(gm.d_mu_d_p(0, X), om.d_mu_d_p(0, X), ystd[0] / pd) < TOL_MEAN
+    assert helpers.relerr(gm.d_s2_d_p(0, X), om.d_s2_d_p(0, X), vscale[0] / pd) < TOL_VAR
+    assert helpers.relerr(gm.d2_s2_d_p2(0, X), om.d2_s2_d_p2(0, X), vscale[0] / np.outer(pd, pd)) < TOL_D2S2
