@@ -34,3 +34,29 @@ def relerr(a, b, scale=None):
     den = np.abs(b) if scale is None else np.maximum(np.abs(b), scale)
     den = np.where(den == 0, 1.0, den)
     return float(np.max(np.abs(a - b) / den))
+
+
+def variance_derivatives_factor_form(om, e, Xt):
+    """d s2 / d p and d2 s2 / d p2 (transformed units, no binary variables) recomputed in FP64 through triangular
+    solves against the Cholesky factor instead of GPy's explicit K^-1 (gp_model.py:263, GPy predictive_gradients).
+    Same mathematics as oracle.model.OracleGPModel._d_s2_d_p / _d2_s2_d_p2, but backward stable: the explicit
+    inverse loses cond(K) * u in the products k^T K^-1 dk, which is what limits the GPy-form oracle at large n."""
+    from scipy.linalg import solve_triangular
+    gp = om.gps[e][0]
+    gpX, L = gp._predictive_variable, gp.posterior.woodbury_chol
+    dx = om.dim_x
+    Z = om.get_Z(Xt)
+    kp = gp.kern.kernp
+    kx = gp.kern.kernx.K(Z, gpX)
+    Zs, Xs = Z[:, kp.active_dims], gpX[:, kp.active_dims]
+    rr = kp._scaled_dist_sliced(Zs, Xs)
+    w = kp._inv_dist_sliced(Zs, Xs) * (kp.dK_dr(rr) * kx)
+    dk = w[:, :, None] * (Zs[:, None, :] - Xs[None, :, :]) / kp.lengthscale ** 2          # (N, n, P)
+    k = gp.kern.K(Z, gpX)
+    v = solve_triangular(L, k.T, lower=True)                                               # (n, N)
+    W = np.stack([solve_triangular(L, dk[:, :, a].T, lower=True) for a in range(dk.shape[2])], axis=2)   # (n, N, P)
+    ds2 = -2.0 * np.einsum('in,ina->na', v, W)
+    beta = solve_triangular(L, v, lower=True, trans='T').T                                  # (N, n) = k K^-1
+    ddk = np.sum(kp.gradients_XX(-kx * beta, Z, gpX), axis=1)[:, dx:, dx:]
+    d2s2 = -2.0 * (ddk + np.einsum('ina,inb->nab', W, W))
+    return ds2, d2s2

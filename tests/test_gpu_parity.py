@@ -443,7 +443,14 @@ def test_tail_overlap_is_bit_identical_and_matches_the_oracle(gpu_ctx):
 @pytest.mark.parametrize('kernel,n', [('Matern52', 4000), ('RBF', 2100)])
 def test_large_training_set_parity(kernel, n, gpu_ctx):
     """n_train of the C3-C5 configs (n_pad = 4096: 32 row blocks, 96 padding rows trimmed, 4 x 16 k pipeline) and an
-    ill-conditioned RBF factor with a ragged size, on a candidate sample the oracle finishes in seconds."""
+    ill-conditioned RBF factor with a ragged size, on a candidate sample the oracle finishes in seconds.
+
+    Means, variances and mean derivatives hold the north-star 1e-9.  The variance derivatives of the GPy-form oracle
+    go through the explicit inverse K^-1 (gp_model.py:263) and lose cond(K) * u there (measured on B200 against this
+    oracle: 1.2e-9 / 1.5e-8 at n = 4000 Matern52, 4e-8 / 2.5e-7 at n = 2100 RBF); the CUDA path contracts against
+    L^-1.  They are therefore pinned at 1e-9 / 1e-8 against the same formulas evaluated through triangular solves
+    (helpers.variance_derivatives_factor_form), and the GPy-form numbers are required to agree with both at the
+    conditioning-limited level."""
     oms, ds = helpers.oracle_models(91, M=1, E=1, D=3, P=3, n=n, kernel=kernel)
     gm = helpers.gpu_models(oms)[0]
     om = oms[0]
@@ -456,5 +463,14 @@ def test_large_training_set_parity(kernel, n, gpu_ctx):
     assert helpers.relerr(M1, M0, ystd) < TOL_MEAN
     assert helpers.relerr(S1, S0, vscale) < TOL_VAR
     assert helpers.relerr(gm.d_mu_d_p(0, X), om.d_mu_d_p(0, X), ystd[0] / pd) < TOL_MEAN
-    assert helpers.relerr(gm.d_s2_d_p(0, X), om.d_s2_d_p(0, X), vscale[0] / pd) < TOL_VAR
-    assert helpers.relerr(gm.d2_s2_d_p2(0, X), om.d2_s2_d_p2(0, X), vscale[0] / np.outer(pd, pd)) < TOL_D2S2
+    Xt = om.trans_x(X)
+    kss = vscale[0] / om.ystd[0] ** 2                     # transformed units
+    ds2_f, d2s2_f = helpers.variance_derivatives_factor_form(om, 0, Xt)
+    ds2_g, d2s2_g = gm._d_s2_d_p(0, Xt), gm._d2_s2_d_p2(0, Xt)
+    ds2_o, d2s2_o = om._d_s2_d_p(0, Xt), om._d2_s2_d_p2(0, Xt)
+    e1, e2 = helpers.relerr(ds2_g, ds2_f, kss), helpers.relerr(d2s2_g, d2s2_f, kss)
+    o1, o2 = helpers.relerr(ds2_o, ds2_f, kss), helpers.relerr(d2s2_o, d2s2_f, kss)
+    print('%s n=%d: CUDA vs factor form %.1e / %.1e; GPy-form oracle vs factor form %.1e / %.1e' % (kernel, n, e1, e2, o1, o2))
+    assert e1 < TOL_VAR and e2 < TOL_D2S2
+    assert o1 < 1e-6 and o2 < 1e-5
+    assert helpers.relerr(ds2_g, ds2_o, kss) < 1e-6 and helpers.relerr(d2s2_g, d2s2_o, kss) < 1e-5
