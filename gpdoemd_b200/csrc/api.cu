@@ -557,7 +557,7 @@ static int run_chunk(gpd_ctx* c, Plan& pl, const double* X_dev, int ldx, int nc)
                     Span sp(c, F_TRI, 1, flb);
                     GPD_TRY(launch_tri(s, pl.views_dev, pl.items_dev + grp.item_begin, grp.item_count, 1, nrhs, 1, 1,
                                        pl.panels_out, pl.panels_beta, nullptr, 0, nc, c->num_sms, c->tri_variant, tri_cps_for(c, pl),
-                                       0));
+                                       c->tri_trim));
                 }
                 Span sp(c, F_EVAL, 1, 0);
                 GPD_TRY(launch_beta_contract(s, pl.views_dev, pl.items_dev + grp.item_begin, grp.item_count, X_dev, ldx, nc,

@@ -339,6 +339,8 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) tri_kernel(const TriArgs args
                             else if (BWD ? (klo >= rhi) : (khi <= rlo)) mode = 1;
                             else mode = 2;
                         }
+                        // backward pass: k columns n..n_pad of the last k block multiply zero rows of V
+                        if (BWD && args.trim && q == len - 1 && (nblk - 1) * kBlk + (c + cc) * kChunkK >= g.n) mode = 0;
                         if (mode == 1) compute_chunk<WM, WN, false, BWD>(sA, sB, lane, wm, wn, c + cc, acc);
                         else if (mode == 2) compute_chunk<WM, WN, true, BWD>(sA, sB, lane, wm, wn, c + cc, acc);
                         else if (kTrimOk && mode == 3) compute_chunk<WM, WN, false, BWD, 1>(sA, sB, lane, wm, wn, c + cc, acc);

@@ -148,3 +148,40 @@ def test_jitchol_retry_on_the_device(gpu_ctx):
     Ky = _K_diff(kern, Z) + np.eye(n) * (1e-8 + gp.jitter)
     assert np.max(np.abs(L.dot(L.T) - Ky)) / 1e10 < 1e-12
     assert np.all(np.isfinite(post.woodbury_vector))
+
+
+@pytest.mark.gpu
+def test_build_and_loglik_error_paths(gpu_ctx):
+    """C-ABI error behaviour of the new entry points: non-zero status + message, nothing computed, no fallback."""
+    import ctypes as C
+    from gpdoemd_b200 import kernels
+    from gpdoemd_b200._lib import GpdError, check, dptr
+    from gpdoemd_b200.gp_state import DeviceExactGP, GPState, ProductKernel
+    lib = gpu_ctx.lib
+    rng = np.random.default_rng(1)
+    Z, Y = rng.uniform(size=(30, 3)), rng.normal(size=(30, 1))
+    gp = DeviceExactGP(Z, Y, ProductKernel(kernels.Matern32(2, [0, 1], 'kernx'), kernels.Matern32(1, [2], 'kernp')))
+    st = GPState.from_gp(gp, 2, 1, with_posterior=False)
+    with pytest.raises(GpdError, match='negative noise'):
+        st.build(gpu_ctx, Y[:, 0], -1.0)
+    d = st._desc()
+    d.factor_kind = 1                                                 # GPD_FACTOR_ROOT is not something to build
+    h = C.c_void_p()
+    y = np.ascontiguousarray(Y[:, 0])
+    assert lib.gpd_gp_build(gpu_ctx.handle, C.byref(d), dptr(y), 1e-3, C.byref(h), None, None, None) != 0
+    assert b'Cholesky' in lib.gpd_last_error() and not h.value
+    with pytest.raises(AssertionError):
+        st.upload(gpu_ctx)                                            # no posterior to upload
+    st.ls_x[0] = -1.0
+    with pytest.raises(GpdError, match='lengthscale'):
+        st.build(gpu_ctx, Y[:, 0], 1e-3)
+    # gauss_loglik: E out of range, empty observation set
+    Yo, Mo, So = np.zeros((2, 9)), np.zeros((2, 3, 9)), np.tile(np.eye(9), (2, 3, 1, 1))
+    lp, mh = np.empty((2, 3)), np.empty((2, 3))
+    assert lib.gpd_gauss_loglik(gpu_ctx.handle, dptr(Yo), dptr(Mo), dptr(So), 2, 3, 9, dptr(lp), dptr(mh)) != 0
+    assert b'1 <= E <= 8' in lib.gpd_last_error()
+    check(lib.gpd_gauss_loglik(gpu_ctx.handle, None, None, None, 0, 3, 2, None, None))
+    # a singular covariance gives the reference's behaviour class: non-finite log-density, not a crash
+    from gpdoemd_b200 import discrimination_criteria as gdisc
+    lpz, _ = gdisc._loglik(np.zeros((1, 2)), np.zeros((1, 1, 2)), np.zeros((1, 1, 2, 2)))
+    assert not np.isfinite(lpz[0, 0])
