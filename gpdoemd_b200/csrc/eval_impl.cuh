@@ -46,14 +46,16 @@ template <int KERN>
 __device__ __forceinline__ double kappa_of_r2(double r2, double power, const double* __restrict__ tab) {
     if (KERN == 0) return exp_neg_fast(r2, tab);                 // RBF: exp(-r^2/2), r2 already halved
     double r = sqrt(r2);
-    if (KERN == 1) return exp(-r);                               // Exponential
+    if (KERN == 1) return exp_neg_fast(r, tab);                  // Exponential
     if (KERN == 2) {                                             // Matern32
         const double s3 = 1.7320508075688772;
-        return (1.0 + s3 * r) * exp(-s3 * r);
+        const double a = s3 * r;
+        return (1.0 + a) * exp_neg_fast(a, tab);
     }
     if (KERN == 3) {                                             // Matern52
         const double s5 = 2.23606797749979;
-        return (1.0 + s5 * r + 5.0 / 3.0 * (r * r)) * exp(-s5 * r);
+        const double a = s5 * r;
+        return fma(r2, 5.0 / 3.0, 1.0 + a) * exp_neg_fast(a, tab);
     }
     if (KERN == 4) return cos(r);                                // Cosine
     return exp(-power * log1p(0.5 * r2));                        // RatQuad
@@ -73,7 +75,7 @@ __device__ __forceinline__ int eval_col(int s, int j) {
 // training rows per unrolled loop body of eval_kernel: 4 for the RBF kernel's small column buckets (C2: 0.843 -> 0.808 ms against
 // 2; more independent FP64 chains per warp at 25 % occupancy), 2 where the per-row coefficient registers dominate
 template <int KERN, int NCB>
-struct EvalUnroll { static constexpr int value = (KERN == 0 && NCB <= 5) ? GPD_EVAL_UNROLL : 2; };   // others spill at 4
+struct EvalUnroll { static constexpr int value = (KERN <= 3 && NCB <= 5) ? GPD_EVAL_UNROLL : 2; };   // larger buckets spill at 4
 
 template <int NXB, int NCB, int CPT, int RG, int MODE>
 struct EvalSmem {
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
     const int rg = tid / TPG, s = tid % TPG;
     const int n_pad = g.n_pad, nx = g.nx;
     const double power = g.power_x;
-    if (KERN == 0)
+    if (KERN <= 3)                                               // kernels evaluated with exp_neg_fast
         for (int k = tid; k < kExpTabSize; k += kEvalThreads) sTab[k] = kExp2Tab[k];
 
     double xs[CPT][NXB];

@@ -432,6 +432,7 @@ class GPModel:
             ctx.lib.gpd_gp_free(h)
         self._dev_model, self._dev_gps = None, []
         self._dev_pstar = self._dev_sigma = None
+        self._dev_key = None
 
     def __del__(self):
         try:
@@ -472,15 +473,24 @@ class GPModel:
     def _sync_device(self, pstar=None):
         """Make the device model agree with pmean / Sigma (or an explicit transformed p*)."""
         self._ensure_device()
-        ctx = get_context(self._device)
         if pstar is None:
+            # fast path of a design loop: pmean / Sigma unchanged since the last call (compared by content: callers
+            # may mutate the arrays in place)
             assert self.pmean is not None
+            key = (self.pmean.tobytes(), None if self.Sigma is None else self.Sigma.tobytes())
+            if key == getattr(self, '_dev_key', None):
+                return
+        ctx = get_context(self._device)
+        key_after = None
+        if pstar is None:
             pstar = self.trans_p(self.pmean)
+            key_after = key
         pstar = _lib.as_f64(pstar)
         sig = None if self.Sigma is None else _lib.as_f64(self.Sigma)
         same_p = self._dev_pstar is not None and np.array_equal(self._dev_pstar, pstar)
         same_s = (sig is None) or (self._dev_sigma is not None and np.array_equal(self._dev_sigma, sig))
         if same_p and same_s:
+            self._dev_key = key_after if key_after is not None else getattr(self, '_dev_key', None)
             return
         if not same_s:
             # Sigma travels with pmean in the C ABI; send the original-unit pmean that maps to pstar
@@ -489,6 +499,7 @@ class GPModel:
             self._dev_sigma = sig.copy()
         check(ctx.lib.gpd_model_set_pstar(self._dev_model, dptr(pstar)))
         self._dev_pstar = pstar.copy()
+        self._dev_key = key_after            # None after an explicit p* (hooks called with a foreign p)
         self._cache = None
 
     def device_handle(self):
