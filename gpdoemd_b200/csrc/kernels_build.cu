@@ -283,7 +283,10 @@ int launch_kmat(cudaStream_t s, const KmatArgs& a, const double* Z_dev, double* 
 // in-place lower Cholesky of the n x n row-major matrix A (lower triangle read and written); *info_dev = n + 1 on
 // entry (by the caller), 1 + index of the first non-positive pivot on failure
 int launch_cholesky(cudaStream_t s, double* A_dev, int n, int* info_dev, uint64_t* launches) {
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};          // function attributes are per device
+    int attr_dev = 0;
+    GPD_CUDA(cudaGetDevice(&attr_dev));
+    bool& attr_done = attr_done_dev[attr_dev & 63];
     const int diag_smem = kBlk * kCholLd * (int)sizeof(double);
     const int panel_smem = (kBlk * kBlk + kBlk * kPanelLd) * (int)sizeof(double);
     if (!attr_done) {
@@ -309,7 +312,10 @@ int launch_cholesky(cudaStream_t s, double* A_dev, int n, int* info_dev, uint64_
 }
 
 int launch_chol_solve(cudaStream_t s, const double* L_dev, int n, const double* y_dev, double* x_dev) {
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};          // function attributes are per device
+    int attr_dev = 0;
+    GPD_CUDA(cudaGetDevice(&attr_dev));
+    bool& attr_done = attr_done_dev[attr_dev & 63];
     const int smem = (kBlk * kCholLd + kBlk) * (int)sizeof(double);
     if (!attr_done) {
         GPD_CUDA(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

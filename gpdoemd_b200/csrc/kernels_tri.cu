@@ -403,7 +403,10 @@ int tri_row_groups(int variant) { return variant == 1 ? 2 : 4; }
 
 template <int WM, int WN, bool BWD, int CPS>
 static int tri_launch_one(cudaStream_t s, int grid, const TriArgs& args) {
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};          // function attributes are per device
+    int attr_dev = 0;
+    GPD_CUDA(cudaGetDevice(&attr_dev));
+    bool& attr_done = attr_done_dev[attr_dev & 63];
     if (!attr_done) {
         GPD_CUDA(cudaFuncSetAttribute(tri_kernel<WM, WN, BWD, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(TriSmem<CPS>)));
