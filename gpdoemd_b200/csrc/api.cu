@@ -464,10 +464,20 @@ static int tri_cps_for(const gpd_ctx* c, const Plan& pl) {
 }
 
 // run the GP part for one chunk of nc candidates (device X, row stride ldx); results in pl.mb[m]
-static int run_chunk(gpd_ctx* c, Plan& pl, const double* X_dev, int ldx, int nc) {
+// X_host != nullptr: the candidates of this chunk are still on the host (row-major, ldx doubles per row) and are
+// copied into X_dev here, so that the copy of everything but the head tiles can ride on the second stream beside
+// the head's evaluation and triangular launch.
+static int run_chunk(gpd_ctx* c, Plan& pl, double* X_dev, int ldx, int nc, const double* X_host = nullptr) {
     cudaStream_t s = c->stream;
     const int M = (int)pl.models.size();
     const int Nc = pl.chunk;
+    bool any_binary = false;
+    for (int m = 0; m < M; ++m) any_binary = any_binary || pl.models[m]->nb > 0;
+    const bool overlap = pl.head_tiles > 0 && !pl.need_W && nc > pl.head_tiles * kBlk;
+    // rows the main stream needs before its first kernel: all of them when a routing pass reads X, else the head tiles
+    const size_t head_rows = (X_host && overlap && !any_binary) ? (size_t)pl.head_tiles * kBlk : (size_t)nc;
+    if (X_host)
+        GPD_CUDA(cudaMemcpyAsync(X_dev, X_host, sizeof(double) * head_rows * ldx, cudaMemcpyHostToDevice, s));
     const int tiles_used = (nc + kBlk - 1) / kBlk;
     // routing + zero fill for models with binary variables (rows without a GP keep 0: gp_model.py:190-196)
     for (int m = 0; m < M; ++m) {
@@ -486,10 +496,12 @@ static int run_chunk(gpd_ctx* c, Plan& pl, const double* X_dev, int ldx, int nc)
     // count check (identity routing uses chunk_n = nc).
     (void)tiles_used;
     double n2sum = 0;   // algorithmic flops: n^2 per candidate per right-hand side
-    const bool overlap = pl.head_tiles > 0 && !pl.need_W && nc > pl.head_tiles * kBlk;
     if (overlap) {
         GPD_CUDA(cudaEventRecord(c->ev_fork, s));
         GPD_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+        if (X_host && head_rows < (size_t)nc)
+            GPD_CUDA(cudaMemcpyAsync(X_dev + head_rows * ldx, X_host + head_rows * ldx,
+                                     sizeof(double) * ((size_t)nc - head_rows) * ldx, cudaMemcpyHostToDevice, c->stream2));
     }
     for (int pass = 0; pass < (overlap ? 2 : 1); ++pass) {
         // pass 0: all items (or the head tiles) on the main, high-priority stream; pass 1: the remaining tiles on the
@@ -1234,8 +1246,7 @@ static int hooks_host(gpd_model* mo, const double* X, int64_t N, int flags, cons
     cudaStream_t s = c->stream;
     for (int64_t start = 0; start < N; start += pl.chunk) {
         const int nc = (int)std::min<int64_t>(pl.chunk, N - start);
-        GPD_CUDA(cudaMemcpyAsync(X_dev, X + (size_t)start * D, sizeof(double) * (size_t)nc * D, cudaMemcpyHostToDevice, s));
-        GPD_TRY(run_chunk(c, pl, X_dev, D, nc));
+        GPD_TRY(run_chunk(c, pl, X_dev, D, nc, X + (size_t)start * D));
         const ModelBufs& b = pl.mb[0];
         auto down = [&](double* host, const double* dev, size_t per) -> cudaError_t {
             if (!host) return cudaSuccess;
@@ -1328,8 +1339,7 @@ int gpd_marginal(gpd_model* mo, const double* X, int64_t N, int order, double* m
     const double* Sigma_dev = (const double*)((const char*)mo->xf_dev + offsetof(ModelXform, Sigma));
     for (int64_t start = 0; start < N; start += pl.chunk) {
         const int nc = (int)std::min<int64_t>(pl.chunk, N - start);
-        GPD_CUDA(cudaMemcpyAsync(X_dev, X + (size_t)start * D, sizeof(double) * (size_t)nc * D, cudaMemcpyHostToDevice, s));
-        GPD_TRY(run_chunk(c, pl, X_dev, D, nc));
+        GPD_TRY(run_chunk(c, pl, X_dev, D, nc, X + (size_t)start * D));
         const ModelBufs& b = pl.mb[0];
         {
             Span sp(c, F_MARG, order == 2 ? 2 : 1, 0);
@@ -1584,14 +1594,8 @@ static int score_impl(gpd_ctx* c, gpd_model* const* models, int32_t M, const dou
     for (int k = 0; k < nk; ++k) kinds_h[k] = kinds[k];
     for (int64_t start = 0; start < N; start += Nc) {
         const int nc = (int)std::min<int64_t>(Nc, N - start);
-        const double* Xc;
-        if (x_on_device) {
-            Xc = X + (size_t)start * D;
-        } else {
-            GPD_CUDA(cudaMemcpyAsync(X_stage, X + (size_t)start * D, sizeof(double) * (size_t)nc * D, cudaMemcpyHostToDevice, s));
-            Xc = X_stage;
-        }
-        GPD_TRY(run_chunk(c, pl, Xc, D, nc));
+        if (x_on_device) GPD_TRY(run_chunk(c, pl, const_cast<double*>(X) + (size_t)start * D, D, nc));
+        else GPD_TRY(run_chunk(c, pl, X_stage, D, nc, X + (size_t)start * D));
         if (order == 1) {
             Span sp(c, F_MARG, 1, 0);
             GPD_TRY(launch_post1(s, pms_dev, pl.raws_dev, M, E, nc, nc, d_noise, work, kinds_h, nk));

@@ -28,11 +28,13 @@ def _prep(models, criterion, noise_var, pps):
 
 
 def score_designs_multi(models, X, criteria, order=1, noise_var=None, pps=None, return_dc=True, idx_offset=0,
-                        x_dev=None, N=None, dc_dev=None):
+                        x_dev=None, N=None, dc_dev=None, dc_out=None):
     """Several criteria in one pass over the candidates -> {name: (best_index, best_value, dc or None)}.
 
     X is a host (N, dim_x) array, or pass ``x_dev`` (device pointer) and ``N`` for resident candidates
-    (then ``dc_dev`` may be a device pointer to [len(criteria)][N] doubles).
+    (then ``dc_dev`` may be a device pointer to [len(criteria)][N] doubles).  ``dc_out``: optional preallocated
+    C-contiguous float64 array (len(criteria), N) for the criterion vectors, e.g. page-locked memory from
+    ``Context.pinned_empty`` (a pageable destination makes the 8 N bytes per criterion a staged copy).
     """
     dev = models[0]._device
     ctx = get_context(dev)
@@ -44,7 +46,11 @@ def score_designs_multi(models, X, criteria, order=1, noise_var=None, pps=None, 
     if x_dev is None:
         X = _lib.as_f64(X)
         N = len(X)
-        dc = np.empty((nk, N)) if return_dc else None
+        if return_dc and dc_out is not None:
+            assert dc_out.shape == (nk, N) and dc_out.dtype == np.float64 and dc_out.flags['C_CONTIGUOUS']
+            dc = dc_out
+        else:
+            dc = np.empty((nk, N)) if return_dc else None
         xp, x_on_dev = X.ctypes.data_as(C.c_void_p), 0
         dcp, dc_on_dev = (dc.ctypes.data_as(C.c_void_p) if return_dc else None), 0
     else:
