@@ -9,6 +9,7 @@
 //   -> finalize (original units) [-> assemble (Taylor marginal) -> criterion -> argmax]
 #include <cuda_runtime.h>
 #include <math.h>
+#include <nvtx3/nvToolsExt.h>     // header-only NVTX: ranges for `ncu --nvtx --nvtx-include "gpd/..."`
 #include <string.h>
 
 #include <algorithm>
@@ -108,6 +109,11 @@ namespace gpd {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 constexpr double kRbfCoordScaleHost = 0.70710678118654752440;   // == kRbfCoordScale of eval_impl.cuh
+
+struct NvtxRange {                // RAII range, domain-less, name prefix "gpd/"
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct Span {
     gpd_ctx* c;
@@ -471,6 +477,7 @@ static int run_chunk(gpd_ctx* c, Plan& pl, double* X_dev, int ldx, int nc, const
     cudaStream_t s = c->stream;
     const int M = (int)pl.models.size();
     const int Nc = pl.chunk;
+    NvtxRange nvtx_chunk("gpd/run_chunk");
     bool any_binary = false;
     for (int m = 0; m < M; ++m) any_binary = any_binary || pl.models[m]->nb > 0;
     const bool overlap = pl.head_tiles > 0 && !pl.need_W && nc > pl.head_tiles * kBlk;
@@ -1000,6 +1007,7 @@ int gpd_gp_build(gpd_ctx* c, const gpd_gp_desc* d, const double* Y, double noise
     *out = nullptr;
     GPD_CHECK(d->factor_kind == GPD_FACTOR_CHOL, "gpd_gp_build forms the Cholesky factor of an exact GP");
     GPD_CHECK(noise_var >= 0.0, "negative noise variance");
+    NvtxRange nvtx_build("gpd/gp_build");
     gpd_gp* g = nullptr;
     GPD_TRY(gp_create_common(c, d, &g));
     const int n = g->n, dz = g->D + g->P;
@@ -1522,6 +1530,7 @@ static int score_impl(gpd_ctx* c, gpd_model* const* models, int32_t M, const dou
         GPD_CHECK(models[m]->has_sigma, "Sigma is not set on every model");
         maxP = std::max(maxP, models[m]->P);
     }
+    NvtxRange nvtx_score("gpd/score");
     const bool keep_dc = dc_out != nullptr;
     // ---- plan: reuse the previous call's plan and device tables when nothing they depend on has changed ----
     ScoreState* st = c->score_state;

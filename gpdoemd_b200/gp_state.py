@@ -276,6 +276,23 @@ class GPState:
                    power_x=float(np.ravel(getattr(kx, 'power', 2.0))[0]),
                    power_p=float(np.ravel(getattr(kp, 'power', 2.0))[0]))
 
+    # ---- checkpoint of the exported state (the (Z, alpha, L, theta) snapshot is all prediction needs) ----
+    _ARRAYS = ('x_active', 'ls_x', 'ls_p', 'Z', 'alpha', 'L')
+    _SCALARS = ('kernel', 'dim_x', 'dim_p', 'var_x', 'var_p', 'power_x', 'power_p', 'factor_kind')
+
+    def to_dict(self, prefix=''):
+        assert self.alpha is not None, 'nothing to save: the posterior lives on the device only'
+        d = {prefix + k: getattr(self, k) for k in self._ARRAYS}
+        d.update({prefix + k: np.asarray(getattr(self, k)) for k in self._SCALARS})
+        return d
+
+    @classmethod
+    def from_dict(cls, d, prefix=''):
+        g = lambda k: d[prefix + k]
+        return cls(str(g('kernel')), int(g('dim_x')), int(g('dim_p')), g('x_active'), float(g('var_x')), g('ls_x'),
+                   float(g('var_p')), g('ls_p'), g('Z'), g('alpha'), g('L'), power_x=float(g('power_x')),
+                   power_p=float(g('power_p')), factor_kind=int(g('factor_kind')))
+
     def _desc(self):
         d = _lib.GpDesc()
         d.kernel = _lib.KERNEL_IDS[self.kernel]

@@ -453,7 +453,9 @@ class GPModel:
                 if gp is None:
                     handles[e * R + r] = None
                     continue
-                if getattr(gp, 'built_on_device', False):
+                if isinstance(gp, GPState):                       # restored from a state checkpoint
+                    h = gp.upload(ctx)
+                elif getattr(gp, 'built_on_device', False):
                     h = gp.build(ctx, self.dim_x, self.dim_p)
                 else:
                     h = GPState.from_gp(gp, self.dim_x, self.dim_p).upload(ctx)
@@ -608,6 +610,60 @@ class GPModel:
         self.Z = d['Z']
         self.Y = d['Y']
         self.hyp = d['hyp']
+
+    # ---- state checkpoint: everything prediction needs, no GPy / refit on restore ---------------------------
+    def save_state(self, filename):
+        """Write transforms, pmean, Sigma and the exported posterior of every GP (Z, alpha, factor, hyper-parameters)
+        to one ``.npz``.  Unlike ``save`` (model.py:198-241: hyp + raw Z, Y, the GPs are refitted on load) the
+        restored model predicts immediately and bit-identically."""
+        assert self.gps is not None and self.Z is not None and self.Y is not None
+        d = {'meta_name': np.asarray(self.name), 'meta_dims': np.array([self.dim_x, self.dim_p, self.num_outputs]),
+             'meta_binary': np.asarray(self.binary_variables, dtype=int), 'meas_noise_var': np.asarray(self.meas_noise_var),
+             'gp_noise_var': np.asarray(self.gp_noise_var), 'zmin': self.zmin, 'zmax': self.zmax, 'ymean': self.ymean,
+             'ystd': self.ystd, 'sparse': np.asarray(isinstance(self, SparseGPModel))}
+        if self.pmean is not None:
+            d['pmean'] = self.pmean
+        if self.Sigma is not None:
+            d['Sigma'] = self.Sigma
+        for e, row in enumerate(self.gps):
+            for r, gp in enumerate(row):
+                if gp is None:
+                    continue
+                st = gp if isinstance(gp, GPState) else GPState.from_gp(gp, self.dim_x, self.dim_p)
+                d.update(st.to_dict('gp%d_%d_' % (e, r)))
+        np.savez(filename, **d)
+
+    @classmethod
+    def load_state(cls, filename, device=0):
+        with np.load(filename if str(filename).endswith('.npz') else str(filename) + '.npz') as f:
+            d = {k: f[k] for k in f.files}
+        dim_x, dim_p, E = (int(v) for v in d['meta_dims'])
+        klass = SparseGPModel if bool(d['sparse']) and cls is GPModel else cls
+        mnv = d['meas_noise_var']
+        m = klass({'name': str(d['meta_name']), 'dim_x': dim_x, 'dim_p': dim_p, 'num_outputs': E,
+                   'meas_noise_var': float(mnv) if mnv.ndim == 0 else mnv,
+                   'binary_variables': [int(v) for v in d['meta_binary']], 'gp_noise_var': float(d['gp_noise_var'])},
+                  device=device)
+        m._zmin, m._zmax = d['zmin'], d['zmax']
+        m.trans_z = BoxTransform(m.zmin, m.zmax)
+        m.trans_x = BoxTransform(m.xmin, m.xmax)
+        m.trans_p = BoxTransform(m.pmin, m.pmax)
+        m._ymean, m._ystd = d['ymean'], d['ystd']
+        m.trans_y = MeanTransform(m.ymean, m.ystd)
+        R = 2 ** m.dim_b
+        gps = [[GPState.from_dict(d, 'gp%d_%d_' % (e, r)) if ('gp%d_%d_Z' % (e, r)) in d else None for r in range(R)]
+               for e in range(E)]
+        # the reference's predict() asserts Z, Y and hyp (surrogate_model.py:171-173): restored models carry the
+        # inducing / training inputs of the first GP as a stand-in, hyper-parameters live inside the GP states
+        first = next(g for row in gps for g in row if g is not None)
+        m._Z, m._Y = first.Z, np.zeros((len(first.Z), E))
+        m._gps = gps
+        m._hyp = [[None] * R for _ in range(E)]
+        if 'pmean' in d:
+            m.pmean = d['pmean']
+        if 'Sigma' in d:
+            m.Sigma = d['Sigma']
+        return m
 
     def save(self, filename):
         assert isinstance(filename, str)

@@ -474,3 +474,26 @@ def test_large_training_set_parity(kernel, n, gpu_ctx):
     assert e1 < TOL_VAR and e2 < TOL_D2S2
     assert o1 < 1e-6 and o2 < 1e-5
     assert helpers.relerr(ds2_g, ds2_o, kss) < 1e-6 and helpers.relerr(d2s2_g, d2s2_o, kss) < 1e-5
+
+
+def test_restored_state_predicts_bit_identically(tmp_path, gpu_ctx):
+    """GPModel.save_state / load_state (exported posterior checkpoint): the restored model needs neither GPy nor a
+    refit and reproduces every hook and the fused score bit for bit."""
+    import gpdoemd_b200 as g
+    from gpdoemd_b200 import synthetic
+    oms, ds = helpers.oracle_models(33, M=2, E=2, D=3, P=2, n=90, kernel='Matern52', n_binary=1)
+    gms = helpers.gpu_models(oms)
+    X = synthetic.candidates(3, 260, 3, np.max([d['xlo'] for d in ds], axis=0), np.min([d['xhi'] for d in ds], axis=0),
+                             n_binary=1)
+    rms = []
+    for i, gm in enumerate(gms):
+        fn = str(tmp_path / ('m%d' % i))
+        gm.save_state(fn)
+        rms.append(g.GPModel.load_state(fn))
+    for gm, rm in zip(gms, rms):
+        for a, b in zip(gm.predict(X), rm.predict(X)):
+            assert np.array_equal(a, b)
+        assert np.array_equal(gm.d2_s2_d_p2(1, X), rm.d2_s2_d_p2(1, X))
+    r0 = g.score_designs(gms, X, order=2, criterion='AW', noise_var=0.02)
+    r1 = g.score_designs(rms, X, order=2, criterion='AW', noise_var=0.02)
+    assert r0[0] == r1[0] and np.array_equal(r0[2], r1[2])

@@ -152,3 +152,26 @@ def test_default_device_follows_local_rank(monkeypatch):
     assert context.default_device() == 5
     context.set_default_device(3)
     assert context.default_device() == 3
+
+
+def test_state_checkpoint_roundtrip(tmp_path):
+    """save_state / load_state: the exported posterior of every GP, transforms, pmean and Sigma survive a round trip
+    bit for bit (CPU part; the restored model's predictions are compared on the GPU in test_gpu_parity)."""
+    import gpdoemd_b200 as g
+    from gpdoemd_b200 import synthetic
+    from gpdoemd_b200.gp_state import GPState
+    gms, ds = synthetic.build_models(g.GPModel, 5, 1, 2, 3, 2, 40, 'Matern32', n_binary=1)
+    gm = gms[0]
+    fn = str(tmp_path / 'm0_state')
+    gm.save_state(fn)
+    m2 = g.GPModel.load_state(fn)
+    assert (m2.dim_x, m2.dim_p, m2.num_outputs, m2.binary_variables) == (3, 2, 2, [2])
+    assert np.array_equal(m2.pmean, gm.pmean) and np.array_equal(m2.Sigma, gm.Sigma)
+    assert np.array_equal(m2.zmin, gm.zmin) and np.array_equal(m2.ystd, gm.ystd)
+    for e in range(2):
+        for r in range(2):
+            a, b = GPState.from_gp(gm.gps[e][r], 3, 2), m2.gps[e][r]
+            assert isinstance(b, GPState) and a.kernel == b.kernel and a.factor_kind == b.factor_kind
+            for k in ('x_active', 'ls_x', 'ls_p', 'Z', 'alpha', 'L'):
+                assert np.array_equal(getattr(a, k), getattr(b, k))
+            assert (a.var_x, a.var_p) == (b.var_x, b.var_p)
