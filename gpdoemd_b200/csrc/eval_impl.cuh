@@ -17,6 +17,11 @@
 
 namespace gpd {
 
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+                 : "memory");
+}
+
 // exp(-s) for s >= 0, ~1e-16 relative: -s = (m/256) ln2 + u, |u| <= ln2/512;  e^-s = 2^(m>>8) * 2^((m&255)/256) * e^u
 // with a degree-4 Taylor polynomial for e^u (truncation < 4e-17) and a 256-entry table.  9 FP64 instructions
 // (the library exp() needs ~17 FP64 + ~10 integer ones); the underflow guard is an integer compare on the high
@@ -77,14 +82,19 @@ __device__ __forceinline__ int eval_col(int s, int j) {
 template <int KERN, int NCB>
 struct EvalUnroll { static constexpr int value = (KERN <= 3 && NCB <= 5) ? GPD_EVAL_UNROLL : 2; };   // larger buckets spill at 4
 
-template <int NXB, int NCB, int CPT, int RG, int MODE>
+// DB: the record / G staging buffers are double buffered and filled with cp.async (single-RHS small buckets)
+template <int NXB, int NCB, int CPT, int RG, int MODE, bool DB = false>
 struct EvalSmem {
-    static constexpr int kRows = (NCB > 28) ? 32 : 64;           // training rows per shared-memory stage
+#ifndef GPD_EVAL_ROWS
+#define GPD_EVAL_ROWS 128
+#endif
+    static constexpr int kRows = (NCB > 28) ? 32 : ((NCB <= 5) ? GPD_EVAL_ROWS : 64);   // training rows per shared-memory stage
     static constexpr int RS = (NXB + NCB + 1) & ~1;              // record stride, even (16-byte vector loads)
     static constexpr int kRec = kRows * RS;
-    static constexpr int kG = (MODE == 0) ? kRows * (kMaxP + 1) : 0;
+    static constexpr int kG = (MODE == 0) ? kRows * (DB ? 1 : kMaxP + 1) : 0;
     static constexpr int kRed = (RG > 1) ? kBlk * NCB : 0;
-    static constexpr int kMain = kRec + kG;
+    static constexpr int kStage = kRec + kG;                     // one staging buffer
+    static constexpr int kMain = kStage * (DB ? 2 : 1);
     static constexpr int kDoubles = (kMain > kRed ? kMain : kRed) + kExpTabSize;
 };
 
@@ -94,7 +104,9 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
                                                             int ncols, double* __restrict__ panels,
                                                             const double* __restrict__ beta_panels,
                                                             const RawOut* __restrict__ raws, int ldraw) {
-    using SM = EvalSmem<NXB, NCB, CPT, RG, MODE>;
+    // single right-hand side + small column bucket (the first-order scoring path): staging is double buffered
+    constexpr bool DB = ONE_RHS && MODE == 0 && NCB <= 5;
+    using SM = EvalSmem<NXB, NCB, CPT, RG, MODE, DB>;
     constexpr int RS = SM::RS;
     constexpr int kEvalRows = SM::kRows;
     constexpr int TPG = kBlk / CPT;                              // threads per row group (each covers the 128 candidates)
@@ -102,7 +114,7 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
     constexpr int kEvalUnroll = EvalUnroll<KERN, NCB>::value;
     __shared__ __align__(16) double smem[SM::kDoubles];
     double* sRec = smem;
-    double* sG = smem + SM::kRec;
+    double* sG = smem + SM::kRec;                                // DB: buffer b lives at smem + b * SM::kStage
     double* sRed = smem;                                         // reused after the main loop
     double* sTab = smem + (SM::kDoubles - kExpTabSize);
 
@@ -149,7 +161,36 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
     if (MODE == 0) pan = panels + g.panel_off * nrhs + (size_t)it.tile * nrhs * n_pad * kBlk;
     else bpan = beta_panels + g.panel_off + (size_t)it.tile * n_pad * kBlk;   // beta panels hold one RHS kind
 
+    // DB staging: asynchronous 8-byte copies of the next kEvalRows records while the current ones are consumed.
+    // Padding slots (d >= nx, c >= ncols) are zeroed once and never written again.
+    auto stage_async = [&](int i0, int buf) {
+        double* dRec = smem + buf * SM::kStage;
+        double* dG = dRec + SM::kRec;
+        for (int k = tid; k < kEvalRows * NXB; k += kEvalThreads) {
+            const int row = k / NXB, d = k % NXB;
+            if (d < nx) cp_async8(dRec + row * RS + d, gX + (size_t)(i0 + row) * nx + d);
+        }
+        for (int k = tid; k < kEvalRows * NCB; k += kEvalThreads) {
+            const int c = k / kEvalRows, row = k % kEvalRows;
+            if (c < ncols) cp_async8(dRec + row * RS + NXB + c, gC + (size_t)c * n_pad + i0 + row);
+        }
+        for (int k = tid; k < kEvalRows; k += kEvalThreads) cp_async8(dG + k, gG + i0 + k);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (DB) {
+        for (int k = tid; k < SM::kMain; k += kEvalThreads) smem[k] = 0.0;
+        __syncthreads();
+        stage_async(0, 0);
+    }
     for (int i0 = 0; i0 < n_pad; i0 += kEvalRows) {
+        if (DB) {
+            const int buf = (i0 / kEvalRows) & 1;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();                                     // stage landed; everyone is done with the other buffer
+            if (i0 + kEvalRows < n_pad) stage_async(i0 + kEvalRows, buf ^ 1);
+            sRec = smem + buf * SM::kStage;
+            sG = sRec + SM::kRec;
+        } else {
         __syncthreads();
         for (int k = tid; k < kEvalRows * NXB; k += kEvalThreads) {
             const int row = k / NXB, d = k % NXB;
@@ -166,6 +207,7 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
             }
         }
         __syncthreads();
+        }
 #pragma unroll kEvalUnroll
         for (int ii = rg; ii < kEvalRows; ii += RG) {
             const double* __restrict__ rec = sRec + ii * RS;
