@@ -407,6 +407,7 @@ static int plan_materialize(gpd_ctx* c, Plan& pl, Bump& bump) {
                 v.x_active[d] = g->x_active[d];
                 v.xmin[d] = pl.transformed ? 0.0 : mo->xmin[g->x_active[d]];
                 v.xdiff[d] = pl.transformed ? 1.0 : mo->xmax[g->x_active[d]] - mo->xmin[g->x_active[d]];
+                v.xscale[d] = 1.0 / (v.xdiff[d] * g->ls_x[d]) * (g->kernel == GPD_KERN_RBF ? kRbfCoordScaleHost : 1.0);
             }
             const ModelBufs& b = pl.mb[en.model];
             v.idx = mo->nb ? b.idx + (size_t)en.r * Nc : nullptr;

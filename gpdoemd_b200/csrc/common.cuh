@@ -29,6 +29,7 @@ struct GpView {
     const double* LinvB;         // packed backward factor
     double ls[kMaxXDims];        // x lengthscales of the active dims
     double xmin[kMaxXDims], xdiff[kMaxXDims];
+    double xscale[kMaxXDims];    // 1 / (xdiff * lengthscale) [* sqrt(1/2) for RBF]: candidate -> kernel coordinate
     int x_active[kMaxXDims];
     // routing of this GP inside the current chunk
     const int* idx;              // candidate positions (within chunk) handled by this GP, or null = identity

@@ -141,8 +141,7 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
             double v = 0.0;
             if (d < nx && valid) {
                 const double x = X[(size_t)cand * ldx + g.x_active[d]];
-                v = ((x - g.xmin[d]) / g.xdiff[d]) / g.ls[d];   // trans_x, then GPy's X / lengthscale
-                if (KERN == 0) v *= kRbfCoordScale;
+                v = (x - g.xmin[d]) * g.xscale[d];              // trans_x, then GPy's X / lengthscale, as one multiply
             }
             xs[j][d] = v;
         }
