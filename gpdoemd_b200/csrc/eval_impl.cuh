@@ -88,7 +88,7 @@ struct EvalSmem {
 #ifndef GPD_EVAL_ROWS
 #define GPD_EVAL_ROWS 128
 #endif
-    static constexpr int kRows = (NCB > 28) ? 32 : ((NCB <= 5) ? GPD_EVAL_ROWS : 64);   // training rows per shared-memory stage
+    static constexpr int kRows = (NCB > 28) ? 32 : ((NCB <= 11) ? GPD_EVAL_ROWS : 64);   // training rows per shared-memory stage
     static constexpr int RS = (NXB + NCB + 1) & ~1;              // record stride, even (16-byte vector loads)
     static constexpr int kRec = kRows * RS;
     static constexpr int kG = (MODE == 0) ? kRows * (DB ? 1 : kMaxP + 1) : 0;
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
                                                             const double* __restrict__ beta_panels,
                                                             const RawOut* __restrict__ raws, int ldraw) {
     // single right-hand side + small column bucket (the first-order scoring path): staging is double buffered
-    constexpr bool DB = ONE_RHS && MODE == 0 && NCB <= 5;
+    constexpr bool DB = ONE_RHS && MODE == 0 && NCB <= 11;
     using SM = EvalSmem<NXB, NCB, CPT, RG, MODE, DB>;
     constexpr int RS = SM::RS;
     constexpr int kEvalRows = SM::kRows;
