@@ -58,7 +58,7 @@ struct gpd_ctx {
     uint64_t scratch_limit = 6ull << 30;
     DevBuf scratch, tables, flush;
     uint64_t launches = 0;
-    int tri_variant = 0;
+    int tri_variant = 2;   // 0: 16 warps as 4 x 4 (32 x 32 warp tiles), 1: 8 warps as 2 x 4, 2: 16 warps as 2 x 8 (64 x 16)
     int tri_cps = 0;   // 0 = automatic (by factor size), 1 or 2 = forced chunks per pipeline stage
     int tri_trim = 1;  // skip the all-padding 8-row blocks of the last row block
     // profiling: event pairs recorded without synchronising, resolved in gpd_profile_read
@@ -685,7 +685,7 @@ int gpd_set_option(gpd_ctx* c, const char* name, int64_t value) {
     GPD_CHECK(c && name, "null argument");
     c->epoch++;
     if (!strcmp(name, "tri_variant")) {
-        GPD_CHECK(value == 0 || value == 1, "tri_variant is 0 (16 consumer warps) or 1 (8 consumer warps)");
+        GPD_CHECK(value >= 0 && value <= 2, "tri_variant is 0 (16 warps, 4x4), 1 (8 warps, 2x4) or 2 (16 warps, 2x8)");
         c->tri_variant = (int)value;
         return 0;
     }

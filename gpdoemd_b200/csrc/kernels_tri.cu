@@ -181,6 +181,14 @@ __device__ __forceinline__ void compute_chunk(const double* __restrict__ sA, con
     }
 }
 
+// dense chunk restricted to the first hi (1 .. MB-1) 8-row blocks of the warp (padding rows trimmed, warp-uniform hi)
+template <int WM, int WN, bool BWD, int HI>
+__device__ __forceinline__ void compute_trimmed(int hi, const double* __restrict__ sA, const double* __restrict__ sB, int lane,
+                                                int wm, int wn, int chunk_in_blk, double (&acc)[16 / WM][16 / WN][2]) {
+    if (hi == HI) compute_chunk<WM, WN, false, BWD, HI>(sA, sB, lane, wm, wn, chunk_in_blk, acc);
+    else if constexpr (HI > 1) compute_trimmed<WM, WN, BWD, HI - 1>(hi, sA, sB, lane, wm, wn, chunk_in_blk, acc);
+}
+
 // Chunk-stream generator run by ONE thread per CTA (lane 0 of warp 0): walks the flat sequence of
 // (work item, row block I, k block q, chunk c) and issues the two 16 KiB bulk copies of each chunk.
 // The packed factor stores the chunks of one item in exactly this order, so the A address is sequential.
@@ -251,7 +259,7 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) tri_kernel(const TriArgs args
     constexpr int kStages = TriCfg<CPS>::kStages;
     constexpr int kCps = CPS;
     constexpr int MB = 16 / WM, NB = 16 / WN;
-    constexpr bool kTrimOk = !BWD && MB == 4 && !GPD_TRI_CYCLIC;
+    constexpr bool kTrimOk = !BWD && !GPD_TRI_CYCLIC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TriSmem<CPS>& sm = *reinterpret_cast<TriSmem<CPS>*>(smem_raw);
 
@@ -343,9 +351,7 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) tri_kernel(const TriArgs args
                         if (BWD && args.trim && q == len - 1 && (nblk - 1) * kBlk + (c + cc) * kChunkK >= g.n) mode = 0;
                         if (mode == 1) compute_chunk<WM, WN, false, BWD>(sA, sB, lane, wm, wn, c + cc, acc);
                         else if (mode == 2) compute_chunk<WM, WN, true, BWD>(sA, sB, lane, wm, wn, c + cc, acc);
-                        else if (kTrimOk && mode == 3) compute_chunk<WM, WN, false, BWD, 1>(sA, sB, lane, wm, wn, c + cc, acc);
-                        else if (kTrimOk && mode == 4) compute_chunk<WM, WN, false, BWD, (MB > 2 ? 2 : 1)>(sA, sB, lane, wm, wn, c + cc, acc);
-                        else if (kTrimOk && mode == 5) compute_chunk<WM, WN, false, BWD, (MB > 3 ? 3 : 1)>(sA, sB, lane, wm, wn, c + cc, acc);
+                        else if (kTrimOk && mode >= 3) compute_trimmed<WM, WN, BWD, MB - 1>(mode - 2, sA, sB, lane, wm, wn, c + cc, acc);
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stage]));
@@ -399,7 +405,7 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) tri_kernel(const TriArgs args
     }
 }
 
-int tri_row_groups(int variant) { return variant == 1 ? 2 : 4; }
+int tri_row_groups(int variant) { return variant == 0 ? 4 : 2; }
 
 template <int WM, int WN, bool BWD, int CPS>
 static int tri_launch_one(cudaStream_t s, int grid, const TriArgs& args) {
@@ -438,6 +444,11 @@ int launch_tri(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int
     long long nwork = (long long)nitems * nwork_rhs;
     int grid = (int)(nwork < num_sms ? nwork : num_sms);
 #define GPD_TRI_GO(WM, BWD, CPS) return tri_launch_one<WM, 4, BWD, CPS>(s, grid, args)
+    if (variant == 2) {   // 16 warps as 2 row groups x 8 candidate groups (64 x 16 warp tiles)
+        if (backward) { if (cps == 2) return tri_launch_one<2, 8, true, 2>(s, grid, args); return tri_launch_one<2, 8, true, 1>(s, grid, args); }
+        if (cps == 2) return tri_launch_one<2, 8, false, 2>(s, grid, args);
+        return tri_launch_one<2, 8, false, 1>(s, grid, args);
+    }
     if (variant == 1) {
         if (backward) { if (cps == 2) GPD_TRI_GO(2, true, 2); GPD_TRI_GO(2, true, 1); }
         if (cps == 2) GPD_TRI_GO(2, false, 2);

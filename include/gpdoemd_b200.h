@@ -80,7 +80,8 @@ void gpd_destroy(gpd_ctx* ctx);
 const char* gpd_last_error(void);
 /* bytes of per-context scratch the fused paths may use for the K(x*,X) / L^-1 K panels (default 6 GiB) */
 int  gpd_set_scratch_bytes(gpd_ctx* ctx, uint64_t bytes);
-/* tuning knobs: "tri_variant" 0 = 16 warps (32x32 warp tiles), 1 = 8 warps (64x32);
+/* tuning knobs: "tri_variant" 0 = 16 warps as 4x4 (32x32 warp tiles), 1 = 8 warps as 2x4 (64x32), 2 (default) = 16 warps
+ * as 2x8 (64x16: two row groups halve the idle time of the low row groups in the diagonal tiles);
  * "tri_cps" 0 = automatic, 1 = 4 pipeline stages of 16 k, 2 = 3 stages of 32 k;
  * "tail_overlap" 1 (default) = first-order path: the candidate tiles that would form the last, partial wave of the
  *   persistent triangular kernel are evaluated and contracted first, concurrently with the evaluation of the rest;

@@ -9,7 +9,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--config', default='C2')
 ap.add_argument('--candidates', type=int, default=None)
 ap.add_argument('--steps', type=int, default=2)
-ap.add_argument('--tri-variant', type=int, default=0)
+ap.add_argument('--tri-variant', type=int, default=2)
 a = ap.parse_args()
 cfg = dict(synthetic.CONFIGS[a.config])
 N = a.candidates or cfg['N']
