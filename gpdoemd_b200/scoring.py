@@ -20,11 +20,29 @@ from .context import default_device, get_context
 from .design_criteria import _reshape
 
 
+_NORM_CACHE = {}
+
+
+def _norm_key(v):
+    if v is None or isinstance(v, (int, float)):
+        return v
+    a = np.asarray(v, dtype=float)
+    return (a.shape, a.tobytes())
+
+
 def _prep(models, criterion, noise_var, pps):
     M, E = len(models), models[0].num_outputs
-    _, _, noise, pps_n, _, _, _ = _reshape(np.zeros((1, M, E)), np.zeros((1, M, E, E)), noise_var, pps)
+    # noise / prior normalisation of design_criteria._reshape (:202-238), memoised: a design loop passes the same
+    # measurement noise and priors on every call
+    key = (M, E, _norm_key(noise_var), _norm_key(pps))
+    hit = _NORM_CACHE.get(key)
+    if hit is None:
+        _, _, noise, pps_n, _, _, _ = _reshape(np.zeros((1, M, E)), np.zeros((1, M, E, E)), noise_var, pps)
+        if len(_NORM_CACHE) > 64:
+            _NORM_CACHE.clear()
+        hit = _NORM_CACHE[key] = (_lib.as_f64(noise).copy(), _lib.as_f64(pps_n).copy())
     handles = (C.c_void_p * M)(*[m.device_handle() for m in models])
-    return _lib.CRITERION_IDS[criterion], _lib.as_f64(noise), _lib.as_f64(pps_n), handles
+    return _lib.CRITERION_IDS[criterion], hit[0], hit[1], handles
 
 
 def score_designs_multi(models, X, criteria, order=1, noise_var=None, pps=None, return_dc=True, idx_offset=0,
