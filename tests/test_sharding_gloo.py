@@ -55,7 +55,7 @@ def test_two_rank_argmax_allgather(N):
     s.bind(('127.0.0.1', 0))
     port = s.getsockname()[1]
     s.close()
-    mgr = mp.Manager()
+    mgr = mp.get_context('spawn').Manager()      # no fork() of this multi-threaded test process
     out = mgr.dict()
     mp.spawn(_worker, args=(2, port, N, 5, out), nprocs=2, join=True)
     assert len(out) == 2
