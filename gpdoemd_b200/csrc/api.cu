@@ -377,7 +377,7 @@ static int plan_materialize(gpd_ctx* c, Plan& pl, Bump& bump) {
     // views, grouped so that each eval launch sees a contiguous item range
     std::vector<GpView> views(pl.entries.size());
     std::vector<Item> items;
-    long long off = 0;
+    long long off = 0, off_w = 0;
     for (auto& grp : pl.groups) {
         grp.item_begin = (int)items.size();
         for (int ei : grp.entries) {
@@ -386,6 +386,9 @@ static int plan_materialize(gpd_ctx* c, Plan& pl, Bump& bump) {
             gpd_model* mo = pl.models[en.model];
             en.panel_off = off;
             off += (long long)pl.tiles * g->n_pad * kBlk;
+            const long long kinds_g = pl.need_W ? 1 + g->P : 1;     // right-hand-side kinds of this GP's model
+            const long long my_off_w = off_w;
+            off_w += (long long)pl.tiles * g->n_pad * kBlk * kinds_g;
             GpView& v = views[ei];
             memset(&v, 0, sizeof(v));
             v.kernel = g->kernel;
@@ -415,6 +418,7 @@ static int plan_materialize(gpd_ctx* c, Plan& pl, Bump& bump) {
             v.out_e = en.e;
             v.model = en.model;
             v.panel_off = en.panel_off;
+            v.panel_off_w = my_off_w;
             for (int t = 0; t < pl.tiles; ++t) items.push_back(Item{ei, t});
         }
         grp.item_count = (int)items.size() - grp.item_begin;

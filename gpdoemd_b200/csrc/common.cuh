@@ -36,7 +36,9 @@ struct GpView {
     const int* count;            // device count of those positions, or null = chunk size
     int out_e;                   // output row e of the owning model
     int model;                   // model slot inside the current call
-    long long panel_off;         // offset of this GP's panel region, in doubles per RHS kind
+    long long panel_off;         // offset of this GP's region in a ONE-kind panel buffer (first order, beta), in doubles
+    long long panel_off_w;       // offset in a buffer holding this GP's own 1 + P kinds per tile (variance derivatives):
+                                 // rival models may differ in P, so this is NOT panel_off * kinds
 };
 
 // Work item of the evaluation / triangular kernels: GP + candidate tile (128 columns).

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
     const double* __restrict__ gG = g.G;
     double* __restrict__ pan = nullptr;
     const double* __restrict__ bpan = nullptr;
-    if (MODE == 0) pan = panels + g.panel_off * nrhs + (size_t)it.tile * nrhs * n_pad * kBlk;
+    if (MODE == 0) pan = panels + (nrhs == 1 ? g.panel_off : g.panel_off_w) + (size_t)it.tile * nrhs * n_pad * kBlk;
     else bpan = beta_panels + g.panel_off + (size_t)it.tile * n_pad * kBlk;   // beta panels hold one RHS kind
 
     // DB staging: asynchronous 8-byte copies of the next kEvalRows records while the current ones are consumed.

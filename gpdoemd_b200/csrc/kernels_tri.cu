@@ -211,7 +211,8 @@ __device__ __forceinline__ void stream_seek_item(ChunkStream& ps, const TriArgs&
         if (it.tile * kBlk >= count) continue;
         ps.nblk = g.nblk;
         ps.A = BWD ? g.LinvB : g.LinvF;
-        ps.B = args.panels_in + g.panel_off * args.in_stride + ((size_t)(it.tile * args.in_stride + a) * g.n_pad) * kBlk;
+        ps.B = args.panels_in + (args.in_stride == 1 ? g.panel_off : g.panel_off_w) +
+               ((size_t)(it.tile * args.in_stride + a) * g.n_pad) * kBlk;
         ps.total = (int)packed_tiles(g.nblk) * kChunksPerBlk;
         ps.j = 0;
         ps.I = 0;
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) tri_kernel(const TriArgs args
         if (it.tile * kBlk >= count) continue;
         const int nblk = g.nblk, n_pad = g.n_pad;
         double* Out = args.panels_out
-                          ? args.panels_out + g.panel_off * args.out_stride +
+                          ? args.panels_out + (args.out_stride == 1 ? g.panel_off : g.panel_off_w) +
                                 ((size_t)(it.tile * args.out_stride + a) * n_pad) * kBlk
                           : nullptr;
         double csq[NB][2];
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(2 * kBlk) gram_kernel(const GpView* __restrict
     if (it.tile * kBlk >= count) return;
     const int t = threadIdx.x & (kBlk - 1), rg = threadIdx.x >> 7;
     const int n_pad = g.n_pad;
-    const double* base = panels + g.panel_off * NR + ((size_t)it.tile * NR * n_pad) * kBlk;
+    const double* base = panels + g.panel_off_w + ((size_t)it.tile * NR * n_pad) * kBlk;
     double acc[NG];
 #pragma unroll
     for (int k = 0; k < NG; ++k) acc[k] = 0.0;

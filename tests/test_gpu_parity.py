@@ -497,3 +497,40 @@ def test_restored_state_predicts_bit_identically(tmp_path, gpu_ctx):
     r0 = g.score_designs(gms, X, order=2, criterion='AW', noise_var=0.02)
     r1 = g.score_designs(rms, X, order=2, criterion='AW', noise_var=0.02)
     assert r0[0] == r1[0] and np.array_equal(r0[2], r1[2])
+
+
+@pytest.mark.parametrize('seed', range(24))
+def test_randomised_configurations_against_the_oracle(seed, gpu_ctx):
+    """Differential test over random shapes: kernel class, number of design / parameter dimensions (every nx and
+    column bucket of the evaluation kernel), outputs, rival models with different dim_p, a binary design variable,
+    Taylor order and criterion -- fused score vs the oracle's taylor_* + criterion on the same inputs."""
+    import gpdoemd_b200 as g
+    from gpdoemd_b200 import synthetic
+    rng = np.random.default_rng(1000 + seed)
+    kernel = ['RBF', 'Exponential', 'Matern32', 'Matern52', 'RatQuad'][seed % 5]
+    D = int(rng.integers(1, 7))
+    nb = int(rng.integers(0, 2)) if D >= 2 else 0
+    M, E = int(rng.integers(1, 5)), int(rng.integers(1, 5))
+    order = 1 + int(rng.integers(0, 2))
+    P = [int(rng.integers(1, 7 if order == 1 else 4)) for _ in range(M)]
+    n, N = int(rng.integers(20, 161)), int(rng.integers(1, 301))
+    crit = ['HR', 'BH', 'BF', 'AW', 'JR'][int(rng.integers(0, 5))]
+    noise = float(rng.uniform(0.005, 0.05))
+    oms, ds = helpers.oracle_models(500 + seed, M=M, E=E, D=D, P=P, n=n, kernel=kernel, n_binary=nb, gp_noise=1e-4)
+    gms = helpers.gpu_models(oms)
+    lo = np.max([d['xlo'] for d in ds], axis=0)
+    hi = np.min([d['xhi'] for d in ds], axis=0)
+    X = synthetic.candidates(seed, N, D, lo, hi, n_binary=nb)
+    marg = omarg.taylor_first_order if order == 1 else omarg.taylor_second_order
+    mu = np.zeros((N, M, E))
+    S = np.zeros((N, M, E, E))
+    for i, om in enumerate(oms):
+        mu[:, i], S[:, i] = marg(om, X)
+    d0 = ocrit.CRITERIA[crit](mu, S, noise, None)
+    bi, bv, d1 = g.score_designs(gms, X, order=order, criterion=crit, noise_var=noise)
+    info = '%s D=%d nb=%d M=%d E=%d P=%s n=%d N=%d order=%d %s' % (kernel, D, nb, M, E, P, n, N, order, crit)
+    # JR is a difference of O(E) logarithms (exactly 0 for a single model): its natural scale is 1, not its mean
+    scale = max(np.abs(d0).mean(), 1.0 if crit == 'JR' else 1e-300)
+    assert helpers.relerr(d1, d0, scale) < TOL_CRIT, info
+    j = int(np.argmax(d0))
+    assert bi == j or abs(d0[bi] - d0[j]) <= 1e-9 * scale, info      # identical argmax (up to an exact numerical tie)
