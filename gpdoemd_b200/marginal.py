@@ -25,6 +25,7 @@ def _device_marginal(model, xnew, order):
     X = _lib.as_f64(xnew)
     assert X.ndim == 2 and X.shape[1] == model.dim_x
     N, E = len(X), model.num_outputs
+    model.check_routing(X)
     M = np.empty((N, E))
     S = np.empty((N, E, E))
     ctx = get_context(model._device)

@@ -512,10 +512,25 @@ class GPModel:
     # ---- hooks (transformed units) = the device boundary ---------------------------------------
     _FLAG_KEYS = ('dmu', 'd2mu', 'ds2', 'd2s2')
 
+    def check_routing(self, Xt):
+        """The reference dereferences ``self.gps[e][r]`` for every binary combination r that occurs among the designs
+        (gp_model.py:193-199) and dies with AttributeError when no training row had that combination (gps[e][r] is
+        None, :111-113).  The device would leave such rows at zero, so the same error is raised here first."""
+        if self.dim_b == 0 or all(gp is not None for row in self.gps for gp in row):
+            return
+        _, J = binary_dimensions(np.asarray(Xt), self.binary_variables)
+        present = np.unique(J.astype(int))
+        for e, row in enumerate(self.gps):
+            for r in present:
+                if row[r] is None:
+                    raise AttributeError("'NoneType' object has no attribute 'predict_noiseless' (no GP for output %d, "
+                                         "binary combination %d: no training row has it)" % (e, r))
+
     def _hooks(self, Xt, pstar, want):
         """All outputs at once for a batch of transformed designs; cached per (X, p*)."""
         Xt = _lib.as_f64(Xt)
         assert Xt.ndim == 2 and Xt.shape[1] == self.dim_x
+        self.check_routing(Xt)
         self._sync_device(pstar)
         key = (Xt.shape, hash(Xt.tobytes()), self._dev_pstar.tobytes())
         c = self._cache

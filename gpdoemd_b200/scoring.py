@@ -64,6 +64,8 @@ def score_designs_multi(models, X, criteria, order=1, noise_var=None, pps=None, 
     if x_dev is None:
         X = _lib.as_f64(X)
         N = len(X)
+        for m in models:
+            m.check_routing(X)            # binary columns are 0 / 1 in both unit systems
         if return_dc and dc_out is not None:
             assert dc_out.shape == (nk, N) and dc_out.dtype == np.float64 and dc_out.flags['C_CONTIGUOUS']
             dc = dc_out
@@ -85,6 +87,8 @@ def score_designs(models, X, order=1, criterion='BH', noise_var=None, pps=None, 
     """-> (best_index, best_value, dc or None).  X: (N, dim_x) host array in original units."""
     X = _lib.as_f64(X)
     N = len(X)
+    for m in models:
+        m.check_routing(X)
     dev = models[0]._device
     ctx = get_context(dev)
     kind, noise, pps_n, handles = _prep(models, criterion, noise_var, pps)

@@ -175,3 +175,21 @@ def test_state_checkpoint_roundtrip(tmp_path):
             for k in ('x_active', 'ls_x', 'ls_p', 'Z', 'alpha', 'L'):
                 assert np.array_equal(getattr(a, k), getattr(b, k))
             assert (a.var_x, a.var_p) == (b.var_x, b.var_p)
+
+
+def test_missing_binary_combination_raises_like_the_reference():
+    """gp_model.py:193-199: a design whose binary combination has no GP (no training row had it) makes the reference
+    dereference None; the product raises the same AttributeError instead of returning zeros from the device."""
+    import gpdoemd_b200 as g
+    from gpdoemd_b200 import synthetic
+    gms, ds = synthetic.build_models(g.GPModel, 7, 1, 1, 3, 2, 30, 'Matern32', n_binary=1)
+    gm = gms[0]
+    gm._gps = [[gm.gps[0][0], None]]                 # as if no training row had b = 1
+    X = synthetic.candidates(1, 10, 3, ds[0]['xlo'], ds[0]['xhi'], n_binary=1)
+    X[:, 2] = 0
+    gm.check_routing(X)                              # only combination 0 occurs: fine
+    X[3, 2] = 1
+    with pytest.raises(AttributeError, match='predict_noiseless'):
+        gm.check_routing(X)
+    with pytest.raises(AttributeError):
+        g.score_designs([gm], X)

@@ -6,6 +6,7 @@ import gpdoemd_b200 as g
 from gpdoemd_b200 import synthetic
 from oracle import criteria as ocrit, marginal as omarg
 lo_s, hi_s = int(sys.argv[1]), int(sys.argv[2])
+SPARSE = len(sys.argv) > 3 and sys.argv[3] == 'sparse'           # SparseGPModel surrogates (VarDTC posterior)
 DEVICE_BUILD = len(sys.argv) > 3 and sys.argv[3] == 'device'     # product models built by gpd_gp_build instead of adopted
 bad = 0
 for seed in range(lo_s, hi_s):
@@ -17,9 +18,15 @@ for seed in range(lo_s, hi_s):
     n, N = int(rng.integers(5, 300)), int(rng.integers(1, 700))
     noise = float(rng.uniform(0.005, 0.05))
     try:
-        oms, ds = helpers.oracle_models(900 + seed, M=M, E=E, D=D, P=P, n=n, kernel=kernel, n_binary=nb, gp_noise=1e-4)
+        if SPARSE:
+            n = max(n, 40)
+            oms, ds = helpers.oracle_sparse_models(900 + seed, M, E, D, P, n, kernel, num_inducing=int(rng.integers(8, 40)), n_binary=nb)
+        else:
+            oms, ds = helpers.oracle_models(900 + seed, M=M, E=E, D=D, P=P, n=n, kernel=kernel, n_binary=nb, gp_noise=1e-4)
         if DEVICE_BUILD:
             gms, _ = synthetic.build_models(g.GPModel, 900 + seed, M, E, D, P, n, kernel, n_binary=nb, gp_noise=1e-4, build_on_device=True)
+        elif SPARSE:
+            gms = [g.SparseGPModel.from_reference(m) for m in oms]
         else:
             gms = helpers.gpu_models(oms)
         lo = np.max([d['xlo'] for d in ds], axis=0); hi = np.min([d['xhi'] for d in ds], axis=0)
@@ -47,7 +54,7 @@ for seed in range(lo_s, hi_s):
             errs['d2mu'] = helpers.relerr(gm.d2_mu_d_p2(e, X), om.d2_mu_d_p2(e, X), ystd[e] / np.outer(pd, pd))
             errs['d2s2'] = helpers.relerr(gm.d2_s2_d_p2(e, X), om.d2_s2_d_p2(e, X), vs[e] / np.outer(pd, pd))
         tol = {'mu': 1e-9, 's2': 1e-9, 'dmu': 1e-9, 'ds2': 1e-9, 'd2mu': 1e-9, 'd2s2': 1e-8}
-        if DEVICE_BUILD:      # two backward-stable factorisations agree to cond * u
+        if DEVICE_BUILD or SPARSE:   # two backward-stable factorisations agree to cond * u; sparse: root of woodbury_inv
             tol = {k: 100 * v for k, v in tol.items()}
         fails = {k: v for k, v in errs.items() if not (v < tol.get(k, 1e-7))}
         tag = 'FAIL' if fails else 'ok'
