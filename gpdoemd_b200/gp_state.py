@@ -225,7 +225,12 @@ def lower_root_of(W):
         if info == 0:
             break
         jitter = scale * 1e-14 if jitter == 0.0 else jitter * 100
-    assert info == 0, 'woodbury_inv is not positive semi-definite'
+    if info != 0:
+        lam = np.linalg.eigvalsh(0.5 * (W + W.T))
+        raise AssertionError('woodbury_inv is not positive semi-definite (eigenvalues %.3g .. %.3g): the sparse posterior '
+                             'is numerically meaningless, K(Z, Z) of the inducing inputs is too ill-conditioned for its '
+                             'hyper-parameters (the reference would return k** - k^T W k of this indefinite W, possibly '
+                             'negative variances)' % (lam[0], lam[-1]))
     return np.ascontiguousarray(np.tril(G)[::-1, ::-1].T)
 
 
