@@ -465,13 +465,12 @@ static int plan_materialize(gpd_ctx* c, Plan& pl, Bump& bump) {
     return 0;
 }
 
-// Pipeline-stage depth of tri_kernel.  Measured on B200 (profiles/r01_summary.md): small factors (C2, n_pad 512)
-// prefer 3 stages of 32 k, large ones (n_pad 4096) 4 stages of 16 k.
+// Pipeline-stage depth of tri_kernel.  Measured on B200 with the 2 x 8 warp layout (profiles/r01_summary.md): 3 stages of
+// 32 k beat 4 stages of 16 k at n_pad = 512 (C2: 5.91 vs 6.00 ms) and at n_pad = 4096 (C5: 0.967 vs 0.956 of the peak);
+// with the earlier 4 x 4 layout the large factors had preferred 4 x 16 k.
 static int tri_cps_for(const gpd_ctx* c, const Plan& pl) {
-    if (c->tri_cps) return c->tri_cps;
-    int max_nblk = 0;
-    for (const auto& en : pl.entries) max_nblk = std::max(max_nblk, en.gp->nblk);
-    return max_nblk <= 8 ? 2 : 1;
+    (void)pl;
+    return c->tri_cps ? c->tri_cps : 2;
 }
 
 // run the GP part for one chunk of nc candidates (device X, row stride ldx); results in pl.mb[m]
