@@ -99,7 +99,11 @@ struct EvalSmem {
 };
 
 template <int KERN, int NXB, int NCB, int CPT, int RG, int MODE, bool ONE_RHS>
-__global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 512 : 1024) / (RG * (kBlk / CPT)) : 1) eval_kernel(const GpView* __restrict__ gps, const Item* __restrict__ items,
+#ifndef GPD_EVAL_CPT_MID
+#define GPD_EVAL_CPT_MID 4        // candidates per thread of the 11-column bucket (first order with P = 6..10)
+#define GPD_EVAL_MINB_MID 1       // resident CTAs per SM the compiler must allow for it
+#endif
+__global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 512 : 1024) / (RG * (kBlk / CPT)) : (NCB <= 11 ? GPD_EVAL_MINB_MID : 1)) eval_kernel(const GpView* __restrict__ gps, const Item* __restrict__ items,
                                                             const double* __restrict__ X, int ldx, int chunk_n, int nrhs,
                                                             int ncols, double* __restrict__ panels,
                                                             const double* __restrict__ beta_panels,
@@ -355,7 +359,7 @@ static int dispatch_cols(cudaStream_t s, int mode, int nitems, int ncols, const 
         if (ncols <= 2) GPD_GO_SMALL(2, 0);
         if (ncols <= 5) GPD_GO_SMALL(5, 0);
         if (ncols <= 8) GPD_GO_SMALL(8, 0);
-        if (ncols <= 11) GPD_GO(11, 4, 0);
+        if (ncols <= 11) GPD_GO(11, GPD_EVAL_CPT_MID, 0);
         if (ncols <= 17) GPD_GO(17, 2, 0);
         if (ncols <= 28) GPD_GO(28, 2, 0);
         if (ncols <= 72) GPD_GO(72, 1, 0);

@@ -15,7 +15,10 @@ cfg = dict(synthetic.CONFIGS[a.config])
 N = a.candidates or cfg['N']
 ctx = g.get_context(0)
 ctx.set_option('tri_variant', a.tri_variant)
-models, ds = synthetic.build_models(g.GPModel, 2, cfg['M'], cfg['E'], cfg['D'], cfg['P'], cfg['n'], cfg['kernel'])
+models, ds = synthetic.build_models(g.GPModel, 2, cfg['M'], cfg['E'], cfg['D'], cfg['P'], cfg['n'], cfg['kernel'],
+                                    build_on_device=cfg['n'] >= 2000)
+if cfg['n'] >= 2000:
+    ctx.set_scratch_bytes(64 << 30)
 lo = np.max([d['xlo'] for d in ds], axis=0)
 hi = np.min([d['xhi'] for d in ds], axis=0)
 X_dev = ctx.dev_alloc(N * cfg['D'] * 8)
