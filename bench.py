@@ -1,14 +1,22 @@
 #!/usr/bin/env python
 """Benchmark of the GPdoemd design-evaluation hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2|C3|C4|C5] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2|C3|C4|C5|S2] [--impl ours|reference]
 
-A "step" = one pass of predict + Taylor marginal + criteria (+ argmax) over one batch of N synthetic
-candidate designs for all M rival models.  Prints ONE JSON line (rank 0).  See DESIGN.md section
-"Measurement" for the definition of every field.
+A "step" = one pass of predict + Taylor marginal + criteria (+ argmax, + the NCCL all-gather of the per-rank winners
+when N > 1) over one batch of synthetic candidate designs for all M rival models.  Prints ONE JSON line (rank 0).
+
+The headline (`value`, `e2e`, `roofline`) is BASELINE configs[1] (C2) with N candidates per GPU (weak scaling).
+The same line carries, nested inside keys the driver keeps whole:
+  roofline.configs       C3 / C4 / C5 at a reduced N of >= 40 complete persistent-kernel waves each: throughput,
+                         tri_kernel fraction of the FP64 peak, pipeline fraction, parity against the CPU oracle and a
+                         small CPU baseline of their own (N = 1 runs only);
+  config.scaling_sweep   BASELINE configs[4] (C5) at a FIXED GLOBAL candidate count cut into contiguous blocks over
+                         the N ranks (strong scaling), the all-gather inside every timed step (every N);
+  cpu_baseline.parity    the CPU leg's own candidate sample scored by the GPU in the same process.
+See DESIGN.md section "Measurement" for the definition of every field.
 """
 import argparse
-import ctypes as C
 import json
 import os
 import subprocess
@@ -16,8 +24,8 @@ import sys
 import threading
 import time
 
-if '--impl' in sys.argv and 'reference' in sys.argv:
-    # the reference arm runs on rank 0 alone and may use every host core; torchrun presets OMP_NUM_THREADS=1
+# torchrun presets OMP_NUM_THREADS=1 for every rank; the CPU legs run on rank 0 alone and may use every host core
+if int(os.environ.get('RANK', '0')) == 0 and (int(os.environ.get('WORLD_SIZE', '1')) > 1 or 'reference' in sys.argv):
     for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
         os.environ[_v] = str(os.cpu_count())
 
@@ -28,6 +36,13 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'candidate designs scored/sec (predict+marginal+criterion, FP64)'
 UNIT = 'designs/s'
+SEED = 2
+NUM_SMS = 148
+NOISE = 0.01
+# reduced candidate counts of the extra configs: tiles x GPs x RHS = a whole number (>= 40) of 148-CTA waves
+EXTRA_N = {'C3': 148 * 128, 'C4': 148 * 128, 'C5': 370 * 128}
+SWEEP_GLOBAL_N = 1 << 18            # C5 strong-scaling sweep: fixed global candidate count
+CPU_SAMPLE = {'C2': 2000, 'C3': 48, 'C4': 128, 'C5': 256, 'S2': 2000}
 
 
 def workload_name(cfg, name):
@@ -37,12 +52,31 @@ def workload_name(cfg, name):
                                       cfg['order'], '/'.join(cfg['criteria'])))
 
 
-def algorithmic_flops_per_candidate(cfg):
-    """per GP n^2 (first order) or (P+2) n^2 (second order) for the triangular contraction,
-    the dominant kernel; the evaluation/criteria terms are reported separately in DESIGN.md."""
+def config_dict(cfg, name, world):
+    """Identical in both arms (the driver compares it)."""
+    return {'workload': workload_name(cfg, name), 'config_id': name, 'global_candidates': cfg['N'] * world,
+            'parallelism': 'candidates sharded x%d (contiguous blocks), GP factors replicated' % world,
+            'l2': 'flushed before every timed step (256 MiB write); panels working set >> L2',
+            'timing': 'value: CUDA events on the library stream around every step, summed, max over ranks; '
+                      'e2e: host perf_counter around the public API call after a device sync, max over ranks'}
+
+
+def tri_flops_per_candidate(cfg):
+    """The dominant kernel's algorithmic work, SURVEY 8(d): n^2 per GP (first order) or (P+2) n^2 (second order)."""
     G = cfg['M'] * cfg['E']
     n, P = cfg.get('inducing') or cfg['n'], cfg['P']
     return G * (n * n if cfg['order'] == 1 else (P + 2) * n * n)
+
+
+def survey_flops_per_candidate(cfg):
+    """SURVEY 8(d) F1 / F2 in full: triangular contraction + mean/derivative contractions + kernel evaluation
+    (c_k = 3 D_active + 45 flops per (candidate, training row), one software exp counted as 40)."""
+    G = cfg['M'] * cfg['E']
+    n, P, D = cfg.get('inducing') or cfg['n'], cfg['P'], cfg['D']
+    ck = 3 * D + 45
+    if cfg['order'] == 1:
+        return G * (n * n + 2 * n * (1 + P) + ck * n)
+    return G * ((P + 2) * n * n + 2 * n * (1 + P + P * (P + 1) // 2) * 2 + ck * n)
 
 
 class ClockSampler(threading.Thread):
@@ -81,42 +115,6 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def cpu_reference_run(cfg, seed, n_sample, steps, warmup):
-    """The reference's CPU algorithm (oracle port: GPy arithmetic restated in NumPy/LAPACK + the
-    reference's Taylor/criteria code) on a bounded sample of the workload, all host threads."""
-    from gpdoemd_b200 import synthetic
-    from oracle import criteria as ocrit
-    from oracle import gpy_kernels
-    from oracle import marginal as omarg
-    from oracle.model import OracleGPModel, OracleSparseGPModel
-    sparse = dict(num_inducing=cfg['inducing'], gp_noise=1e-4) if cfg.get('inducing') else {}
-    oms, ds = synthetic.build_models(OracleSparseGPModel if sparse else OracleGPModel, seed, cfg['M'], cfg['E'], cfg['D'],
-                                     cfg['P'], cfg['n'], cfg['kernel'], kernel_lookup=gpy_kernels.KERNELS, **sparse)
-    lo = np.max([d['xlo'] for d in ds], axis=0)
-    hi = np.min([d['xhi'] for d in ds], axis=0)
-    X = synthetic.candidates(7, n_sample, cfg['D'], lo, hi)
-    marg = omarg.taylor_first_order if cfg['order'] == 1 else omarg.taylor_second_order
-
-    def step():
-        mu = np.zeros((n_sample, cfg['M'], cfg['E']))
-        S = np.zeros((n_sample, cfg['M'], cfg['E'], cfg['E']))
-        for i, om in enumerate(oms):
-            mu[:, i], S[:, i] = marg(om, X)
-        out = {}
-        for cname in cfg['criteria']:
-            dc = ocrit.CRITERIA[cname](mu, S, 0.01, None)
-            out[cname] = int(np.argmax(dc))
-        return out
-
-    for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = time.perf_counter() - t0
-    return n_sample * steps / dt, dt / steps
-
-
 def blas_threads():
     """threads NumPy's BLAS/LAPACK actually uses (the `cores` of cpu_baseline)"""
     try:
@@ -127,10 +125,193 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
-def cpu_sample_size(cfg):
-    # ~10-30 s of CPU work per run: the oracle does ~700 designs/s on C2 (8 cores) and far less on n=4000
-    per = {'C2': 4000, 'C3': 48, 'C4': 64, 'C5': 256, 'S2': 4000}
-    return per
+# ---- the CPU leg: the reference's algorithm (oracle port) on a bounded sample --------------------------------------
+def oracle_models(cfg, seed, adopt_from=None):
+    """Oracle (NumPy/LAPACK) models of the workload.  adopt_from: GPU-side models whose posterior (alpha, L) is shared
+    instead of refactorised (n = 4000: one host Cholesky per GP would take minutes for 64 GPs); the hyper-parameters,
+    training data and transforms are the same either way."""
+    from gpdoemd_b200 import synthetic
+    from oracle import gpy_kernels
+    from oracle.model import OracleGPModel, OracleSparseGPModel, adopt_exact_model
+    if adopt_from is not None:
+        oms = [adopt_exact_model(m) for m in adopt_from]
+        for om in oms:
+            om.want_var_jac = cfg['order'] == 2   # first order: skip the variance Jacobian GPy computes and the reference
+        return oms                                # discards (it needs K^-1 = an n^3 dpotri per GP)
+    sparse = dict(num_inducing=cfg['inducing'], gp_noise=1e-4) if cfg.get('inducing') else {}
+    oms, _ = synthetic.build_models(OracleSparseGPModel if sparse else OracleGPModel, seed, cfg['M'], cfg['E'], cfg['D'],
+                                    cfg['P'], cfg['n'], cfg['kernel'], kernel_lookup=gpy_kernels.KERNELS, **sparse)
+    return oms
+
+
+def oracle_step(cfg, oms, X):
+    from oracle import criteria as ocrit
+    from oracle import marginal as omarg
+    marg = omarg.taylor_first_order if cfg['order'] == 1 else omarg.taylor_second_order
+    mu = np.zeros((len(X), cfg['M'], cfg['E']))
+    S = np.zeros((len(X), cfg['M'], cfg['E'], cfg['E']))
+    for i, om in enumerate(oms):
+        mu[:, i], S[:, i] = marg(om, X)
+    return {c: ocrit.CRITERIA[c](mu, S.copy(), NOISE, None) for c in cfg['criteria']}
+
+
+def cpu_leg(cfg, oms, X, steps, warmup):
+    """-> (designs/s, seconds per step, {criterion: dc}) on the candidates X."""
+    dc = None
+    for _ in range(warmup):
+        dc = oracle_step(cfg, oms, X)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        dc = oracle_step(cfg, oms, X)
+    dt = time.perf_counter() - t0
+    return len(X) * steps / dt, dt / steps, dc
+
+
+def parity_block(dc_gpu, dc_cpu, criteria):
+    """GPU criterion values against the CPU oracle on the same candidates: gate 1e-7 relative (north star), argmax."""
+    worst, match = 0.0, True
+    for c in criteria:
+        a, b = np.asarray(dc_gpu[c], dtype=float), np.asarray(dc_cpu[c], dtype=float)
+        scale = np.maximum(np.abs(b), 1e-6 * max(float(np.median(np.abs(b))), 1e-300))
+        worst = max(worst, float(np.max(np.abs(a - b) / scale)))
+        match = match and int(np.argmax(a)) == int(np.argmax(b))
+    return {'max_rel_err': worst, 'argmax_match': bool(match), 'n': int(len(next(iter(dc_cpu.values())))),
+            'criteria': list(criteria), 'gate': 1e-7, 'ok': bool(worst < 1e-7 and match),
+            'against': 'oracle port (oracle/) on the same candidates, criterion values per candidate'}
+
+
+def sample_rows(N, k, must=()):
+    idx = np.unique(np.r_[np.linspace(0, N - 1, max(2, k - len(must))).astype(np.int64), np.asarray(must, dtype=np.int64)])
+    return idx
+
+
+# ---- the GPU side -------------------------------------------------------------------------------------------------
+class Problem:
+    """Models on this rank's GPU + a resident candidate block + its pinned host copy."""
+
+    def __init__(self, g, ctx, cfg, local_rank, gp_build, N, first_row, want_host=True):
+        from gpdoemd_b200 import synthetic
+        self.g, self.ctx, self.cfg, self.N, self.first_row = g, ctx, cfg, int(N), int(first_row)
+        sparse = dict(num_inducing=cfg['inducing'], gp_noise=1e-4) if cfg.get('inducing') else {}
+        on_dev = (gp_build or ('device' if cfg['n'] >= 2000 else 'host')) == 'device'
+        self.models, ds = synthetic.build_models(g.SparseGPModel if sparse else g.GPModel, SEED, cfg['M'], cfg['E'], cfg['D'],
+                                                 cfg['P'], cfg['n'], cfg['kernel'], device=local_rank,
+                                                 build_on_device=on_dev, **sparse)
+        self.lo = np.max([d['xlo'] for d in ds], axis=0)
+        self.hi = np.min([d['xhi'] for d in ds], axis=0)
+        D = cfg['D']
+        self.X_dev = ctx.dev_alloc(max(self.N, 1) * D * 8)
+        if self.N:
+            ctx.fill_uniform(self.X_dev, self.N, D, seed=20250 + SEED, first_row=self.first_row, lo=self.lo, hi=self.hi)
+        self.X_host = self.dc_host = None
+        if want_host and self.N and self.N * D * 8 <= (4 << 30):
+            self.X_host = ctx.pinned_empty((self.N, D))
+            self.X_host[:] = ctx.dev_download(self.X_dev, (self.N, D))
+            self.dc_host = ctx.pinned_empty((len(cfg['criteria']), self.N))
+        self.crits = list(cfg['criteria'])
+
+    def step_resident(self, scorer=None):
+        kw = dict(order=self.cfg['order'], noise_var=NOISE, return_dc=False, idx_offset=self.first_row, x_dev=self.X_dev, N=self.N)
+        if scorer is not None:
+            return scorer.score_designs_multi(self.models, None, self.crits, **kw)
+        return self.g.score_designs_multi(self.models, None, self.crits, **kw)
+
+    def step_e2e(self, scorer=None):
+        kw = dict(order=self.cfg['order'], noise_var=NOISE, return_dc=True, idx_offset=self.first_row, dc_out=self.dc_host)
+        if scorer is not None:
+            return scorer.score_designs_multi(self.models, self.X_host, self.crits, **kw)
+        return self.g.score_designs_multi(self.models, self.X_host, self.crits, **kw)
+
+    def close(self):
+        self.ctx.dev_free(self.X_dev)
+        for m in self.models:
+            m._invalidate_device()
+        self.models = []
+
+
+def timed_device(ctx, fn, steps, profile=True):
+    """K steps, L2 flushed before each, device time per step from CUDA events on the library stream."""
+    total, res = 0.0, None
+    if profile:
+        ctx.profile_enable(True)
+    for _ in range(steps):
+        ctx.flush_l2()
+        ctx.timer_start()
+        res = fn()
+        total += ctx.timer_stop()
+    prof = ctx.profile_read() if profile else None
+    if profile:
+        ctx.profile_enable(False)
+    return total, res, prof
+
+
+def timed_host(ctx, fn, steps):
+    """End-to-end clock: the L2 flush has COMPLETED (device sync) before the host stopwatch starts; the public API call
+    returns after its own final stream synchronisation, so perf_counter brackets H2D + kernels + D2H."""
+    total, res = 0.0, None
+    for _ in range(steps):
+        ctx.flush_l2()
+        ctx.sync()
+        t0 = time.perf_counter()
+        res = fn()
+        total += time.perf_counter() - t0
+    return total * 1e3, res
+
+
+def measure(prob, steps, warmup, scorer, barrier, reduce_max, want_e2e=True):
+    """Timed resident steps (+ end-to-end steps) of one problem on this rank -> dict (times are max over ranks)."""
+    ctx = prob.ctx
+    res = None
+    for _ in range(warmup):
+        res = prob.step_resident(scorer)
+    barrier()
+    l0 = ctx.launch_count()
+    t_ms, res, prof = timed_device(ctx, lambda: prob.step_resident(scorer), steps)
+    launches = ctx.launch_count() - l0
+    barrier()
+    e2e_ms = 0.0
+    if want_e2e and (prob.X_host is not None or prob.N == 0):
+        for _ in range(2):
+            prob.step_e2e(scorer)
+        barrier()
+        e2e_ms, res_e2e = timed_host(ctx, lambda: prob.step_e2e(scorer), steps)
+        barrier()
+        for c in prob.crits:
+            assert res_e2e[c][0] == res[c][0], 'resident and end-to-end paths disagree on the argmax'
+    nccl_ms = prof['comm']['ms'] if prof else 0.0
+    t_ms, e2e_ms, nccl_ms = reduce_max([t_ms, e2e_ms, nccl_ms])
+    return {'t_ms': t_ms, 'e2e_ms': e2e_ms if want_e2e else None, 'nccl_ms': nccl_ms, 'prof': prof, 'res': res,
+            'launches': launches}
+
+
+def roofline_of(cfg, N_local, steps, ms_per_step, prof, peak, traffic):
+    tri = prof['tri']
+    tri_ms = tri['ms'] / max(1, tri['launches'])
+    achieved = tri['flops'] / max(tri['launches'], 1) / (tri_ms * 1e-3) / 1e12 if tri['launches'] else None
+    # with "tail_overlap" the step has TWO tri_kernel launches: the main one over complete waves (family 'tri', the
+    # dominant kernel reported here) and a small one over the head tiles ('tri_head') that runs concurrently with
+    # the evaluation kernel on a second stream -- the overlapped families' times add up to more than the step
+    return {'bound': 'tensor', 'kernel': 'tri_kernel (FP64 DMMA triangular contraction V = L^-1 K*)',
+            'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak if achieved else None,
+            'traffic': traffic,
+            'algorithmic_flops_per_launch': tri['flops'] / max(tri['launches'], 1),
+            'launch_ms': tri_ms, 'share_of_step': (tri['ms'] / steps) / ms_per_step,
+            'pipeline_frac': tri_flops_per_candidate(cfg) * N_local / (ms_per_step * 1e-3) / 1e12 / peak,
+            'pipeline_frac_survey_flops': survey_flops_per_candidate(cfg) * N_local / (ms_per_step * 1e-3) / 1e12 / peak,
+            'kernel_ms_per_step': {k: v['ms'] / steps for k, v in prof.items() if v['launches']}}
+
+
+def committed_traffic(name, N):
+    """DRAM bytes (read + write) of the dominant launch from the committed ncu capture of the same command, else None."""
+    for f in ('r02_traffic.json', 'r01_traffic.json'):
+        try:
+            tj = json.load(open(os.path.join(ROOT, 'profiles', f)))
+            e = tj.get(name)
+            if e and int(e.get('N', 100000 if name == 'C2' else -1)) == int(N):
+                return e['dram_bytes_read'] + e['dram_bytes_write'], 'profiles/' + f
+        except Exception:
+            pass
+    return None, None
 
 
 def main():
@@ -143,10 +324,14 @@ def main():
     ap.add_argument('--candidates', type=float, default=None, help='override N per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-stepwise', action='store_true', help='skip the informational drop-in-functions leg')
+    ap.add_argument('--no-extra', action='store_true', help='headline only: skip the C3/C4/C5 blocks and the C5 sweep')
+    ap.add_argument('--extra-steps', type=int, default=3, help='timed steps of each C3/C4/C5 block and of the sweep')
+    ap.add_argument('--sweep-candidates', type=float, default=SWEEP_GLOBAL_N)
     ap.add_argument('--tri-variant', type=int, default=None)
     ap.add_argument('--tri-cps', type=int, default=None)
     ap.add_argument('--tri-trim', type=int, default=None)
     ap.add_argument('--tail-overlap', type=int, default=None)
+    ap.add_argument('--option', action='append', default=[], help='name=value, passed to gpd_set_option')
     ap.add_argument('--gp-build', choices=('host', 'device'), default=None,
                     help='where the exact-GP inference (K, Cholesky, alpha) of the setup runs; default: device for '
                          'n_train >= 2000 (16x faster setup at n = 4000), host LAPACK otherwise; outside the timed region')
@@ -167,21 +352,26 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    seed = 2
-    config = {'workload': workload_name(cfg, args.config), 'config_id': args.config,
-              'global_candidates': cfg['N'] * world, 'parallelism': 'candidates sharded x%d, GP factors replicated' % world}
+    config = config_dict(cfg, args.config, world)
+    warmup = max(args.warmup, 3)
 
     if args.impl == 'reference':
+        # the reference's own CPU implementation of the path (oracle port: GPy cannot be installed here), all host
+        # threads, rank 0 alone; every step scores a bounded sample of the workload; K and W are honoured
         if rank != 0:
             return 0
-        ns = cpu_sample_size(cfg)[args.config]
-        steps, warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
-        v, sps = cpu_reference_run(cfg, seed, ns, steps, warm)
-        line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
-                'warmup': warm, 'ms_per_step': sps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        ns = CPU_SAMPLE[args.config]
+        oms = oracle_models(cfg, SEED)
+        lo = np.max([om.xmin for om in oms], axis=0)
+        hi = np.min([om.xmax for om in oms], axis=0)
+        X = synthetic.candidates(7, ns, cfg['D'], lo, hi)
+        v, sps, _ = cpu_leg(cfg, oms, X, args.steps, args.warmup)
+        line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': sps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': config,
                 'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': blas_threads(), 'kind': 'port',
-                                 'sample': '%d candidates per step of the same workload (all models, all criteria)' % ns},
+                                 'sample': '%d candidates per step of the same workload (all models, all criteria), '
+                                           'NumPy/LAPACK threads = %d' % (ns, blas_threads())},
                 'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
         emit(line)
         return 0
@@ -189,182 +379,191 @@ def main():
     import torch
     import gpdoemd_b200 as g
     torch.cuda.set_device(local_rank)
-    dist = None
+    dist = scorer = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     g.set_default_device(local_rank)
     ctx = g.get_context(local_rank)
-    if args.tri_variant is not None:
-        ctx.set_option('tri_variant', args.tri_variant)
-    if args.tri_cps is not None:
-        ctx.set_option('tri_cps', args.tri_cps)
-    if args.tail_overlap is not None:
-        ctx.set_option('tail_overlap', args.tail_overlap)
-    if args.tri_trim is not None:
-        ctx.set_option('tri_trim', args.tri_trim)
-    if (cfg.get('inducing') or cfg['n']) >= 2000:
+    if world > 1:
+        scorer = g.ShardedScorer(device=local_rank)       # the library's own NCCL communicator (gpd_comm_init)
+        torch.cuda.set_device(local_rank)
+    opts = dict(o.split('=') for o in args.option)
+    for k, v in (('tri_variant', args.tri_variant), ('tri_cps', args.tri_cps), ('tail_overlap', args.tail_overlap),
+                 ('tri_trim', args.tri_trim)):
+        if v is not None:
+            opts[k] = v
+    for k, v in opts.items():
+        ctx.set_option(k, int(v))
+    big = (cfg.get('inducing') or cfg['n']) >= 2000
+    if big:
         ctx.set_scratch_bytes(64 << 30)
-
-    # ---- problem: identical GP state on every rank, candidates = this rank's contiguous shard ----------
-    sparse = dict(num_inducing=cfg['inducing'], gp_noise=1e-4) if cfg.get('inducing') else {}
-    models, ds = synthetic.build_models(g.SparseGPModel if sparse else g.GPModel, seed, cfg['M'], cfg['E'], cfg['D'],
-                                        cfg['P'], cfg['n'], cfg['kernel'], device=local_rank,
-                                        build_on_device=(args.gp_build or ('device' if cfg['n'] >= 2000 else 'host')) == 'device',
-                                        **sparse)
-    lo = np.max([d['xlo'] for d in ds], axis=0)
-    hi = np.min([d['xhi'] for d in ds], axis=0)
-    N, D = cfg['N'], cfg['D']
-    first_row = rank * N
-    X_dev = ctx.dev_alloc(N * D * 8)
-    ctx.fill_uniform(X_dev, N, D, seed=20250 + 2, first_row=first_row, lo=lo, hi=hi)
-    X_host = ctx.pinned_empty((N, D)) if N * D * 8 <= (4 << 30) else None
-    if X_host is not None:
-        X_host[:] = ctx.dev_download(X_dev, (N, D))
-    crits = list(cfg['criteria'])
-    noise, order = 0.01, cfg['order']
-
-    def step_resident():
-        return g.score_designs_multi(models, None, crits, order=order, noise_var=noise, return_dc=False,
-                                     idx_offset=first_row, x_dev=X_dev, N=N)
-
-    dc_host = ctx.pinned_empty((len(crits), N)) if X_host is not None else None     # page-locked result buffer
-
-    def step_e2e():
-        return g.score_designs_multi(models, X_host, crits, order=order, noise_var=noise, return_dc=True,
-                                     idx_offset=first_row, dc_out=dc_host)
 
     def barrier():
         if dist is not None:
             dist.barrier()
-        torch.cuda.synchronize()
+        ctx.sync()
 
-    def timed(fn, steps, profile):
-        """K steps, L2 flushed before each, device time per step from CUDA events on the library stream."""
-        total = 0.0
-        res = None
-        if profile:
-            ctx.profile_enable(True)
-        for _ in range(steps):
-            ctx.flush_l2()
-            ctx.timer_start()
-            res = fn()
-            total += ctx.timer_stop()
-        prof = ctx.profile_read() if profile else None
-        if profile:
-            ctx.profile_enable(False)
-        return total, res, prof
+    def reduce_max(vals):
+        if dist is None:
+            return [float(v) for v in vals]
+        torch.cuda.set_device(local_rank)     # the library and torch share the CUDA runtime's current device
+        t = torch.tensor(vals, dtype=torch.float64, device=torch.device('cuda', local_rank))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.cpu()]
 
+    # ---- headline: this rank's contiguous block of N candidates (weak scaling), collective inside every step ----------
+    N, D = cfg['N'], cfg['D']
+    prob = Problem(g, ctx, cfg, local_rank, args.gp_build, N, rank * N)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        res = step_resident()
-    barrier()
-    l0 = ctx.launch_count()
-    t_ms, res, prof = timed(step_resident, args.steps, True)
-    launches = ctx.launch_count() - l0
-    barrier()
+    m = measure(prob, args.steps, warmup, scorer, barrier, reduce_max)
+    clocks_headline = None
+    res, prof = m['res'], m['prof']
+    crits = prob.crits
 
-    e2e_ms = None
-    if X_host is not None:
-        for _ in range(2):
-            step_e2e()
-        barrier()
-        t0 = time.perf_counter()
-        e2e_dev_ms, res_e2e, _ = timed(step_e2e, args.steps, False)
-        barrier()
-        e2e_ms = e2e_dev_ms
-        for c in crits:
-            assert res_e2e[c][0] == res[c][0], 'resident and end-to-end paths disagree on the argmax'
+    # ---- BASELINE configs[4]: C5 strong-scaling sweep, fixed global N, all-gather inside the step (every rank) ---------
+    sweep = None
+    if not args.no_extra and args.config == 'C2' and not args.candidates:
+        c5 = dict(synthetic.CONFIGS['C5'])
+        Ng = int(args.sweep_candidates)
+        lo_i, hi_i = g.scoring.shard_bounds(Ng, rank, world)
+        ctx.set_scratch_bytes(64 << 30)
+        p5 = Problem(g, ctx, c5, local_rank, args.gp_build, hi_i - lo_i, lo_i, want_host=False)
+        m5 = measure(p5, args.extra_steps, 1, scorer, barrier, reduce_max, want_e2e=False)
+        ms5 = m5['t_ms'] / args.extra_steps
+        tiles = -(-(hi_i - lo_i) // 128)
+        sweep = {'config_id': 'C5', 'workload': 'BASELINE configs[4]: M=4, E=4, D=3, P=4, n_train=4000 Matern52, Taylor '
+                                                'order 1 + BH; N=1e8 is cut to a fixed GLOBAL count so that every N finishes in seconds',
+                 'scaling': 'strong', 'global_candidates': Ng, 'n_gpus': world, 'candidates_per_rank': hi_i - lo_i,
+                 'value': Ng / (ms5 * 1e-3), 'unit': UNIT, 'ms_per_step': ms5, 'steps': args.extra_steps,
+                 'nccl_ms_per_step': m5['nccl_ms'] / args.extra_steps,
+                 'collective': ('gpd_score_sharded: pack + ncclAllGather(%d x 16 B) + fold on the library stream, inside every '
+                                'timed step' % world) if world > 1 else 'none (one rank)',
+                 'waves_per_rank': tiles * c5['M'] * c5['E'] / NUM_SMS,
+                 'tri_ms_per_step': m5['prof']['tri']['ms'] / args.extra_steps,
+                 'argmax': {c: int(m5['res'][c][0]) for c in p5.crits}}
+        p5.close()
+        if not big:
+            ctx.set_scratch_bytes(6 << 30)
+    clocks = sampler.stop()      # sampled over warm-up + timed steps + end-to-end steps + the sweep (all under load)
+
+    if rank != 0:
+        if scorer is not None:
+            scorer.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- rank 0 from here on: derived numbers, CPU legs, parity, the single-GPU extra configs ----------------------------
+    peak = ctx.probe_fp64_peak()
+    ms_per_step = m['t_ms'] / args.steps
+    value = N * world / (ms_per_step * 1e-3)
+    traffic, traffic_src = committed_traffic(args.config, N)
+    roofline = roofline_of(cfg, N, args.steps, ms_per_step, prof, peak, traffic)
+    roofline['traffic_source'] = traffic_src
+    roofline['peak_source'] = ('FP64 mma.sync m8n8k4 register-resident probe run in this process (MEASURED_PEAKS.json '
+                               'has no FP64 entry; cuBLAS DGEMM on this pool: 36.1 TFLOP/s, profiles/r01_fp64_peak.jsonl)')
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': config,
+            'roofline': roofline, 'gpu_launches': m['launches'], 'clocks': clocks,
+            'argmax': {c: int(res[c][0]) for c in crits}}
+    if world > 1:
+        line['nccl_ms_per_step'] = m['nccl_ms'] / args.steps
+        line['config']['collective'] = ('gpd_score_sharded: pack + ncclAllGather(%d x %d x 16 B) + fold on the library stream, '
+                                        'inside every timed step' % (world, len(crits)))
+    if m['e2e_ms']:
+        nk = len(crits)
+        line['e2e'] = {'value': N * world / (m['e2e_ms'] / args.steps * 1e-3), 'unit': UNIT,
+                       'h2d_bytes_per_step': world * N * D * 8, 'd2h_bytes_per_step': world * nk * (N * 8 + 16),
+                       'clock': 'host perf_counter around the call, device idle (synchronised) at the start',
+                       'api': 'gpdoemd_b200.score_designs_multi(models, X_host_pinned, criteria, dc_out=pinned) -> dc arrays + argmax'
+                              + (' through ShardedScorer (gpd_score_sharded)' if world > 1 else '')}
 
     # the reference's own call pattern (demos/case_study.py:284-293) through the drop-in functions: one
     # taylor_* call per model (host arrays in and out), then one call per criterion -- informational
-    stepwise_ms = None
-    if X_host is not None and N <= 2000000 and not args.no_stepwise:
-        marg = g.taylor_first_order if order == 1 else g.taylor_second_order
+    if prob.X_host is not None and N <= 2000000 and not args.no_stepwise and world == 1:
+        marg = g.taylor_first_order if cfg['order'] == 1 else g.taylor_second_order
         E, Mn = cfg['E'], cfg['M']
 
         def step_stepwise():
             mu = np.empty((N, Mn, E))
             S = np.empty((N, Mn, E, E))
-            for i, mo in enumerate(models):
-                mu[:, i], S[:, i] = marg(mo, X_host)
-            return {c: int(np.argmax(getattr(g, c)(mu, S, noise, None))) for c in crits}
+            for i, mo in enumerate(prob.models):
+                mu[:, i], S[:, i] = marg(mo, prob.X_host)
+            return {c: int(np.argmax(getattr(g, c)(mu, S, NOISE, None))) for c in crits}
         r_sw = step_stepwise()
-        barrier()
+        ctx.sync()
         t0 = time.perf_counter()
         nsw = max(1, min(3, args.steps))
         for _ in range(nsw):
             r_sw = step_stepwise()
         stepwise_ms = (time.perf_counter() - t0) * 1e3 / nsw
         for c in crits:
-            assert r_sw[c] + first_row == res[c][0], 'drop-in functions and fused path disagree on the argmax'
-    clocks = sampler.stop()      # sampled over warm-up + timed steps + end-to-end steps (all under load)
-
-    # ---- multi-GPU: the only collective is the argmax all-gather; time = max over ranks -----------------
-    best = {c: (res[c][1], res[c][0]) for c in crits}
-    if dist is not None:
-        sc = g.ShardedScorer()
-        torch.cuda.set_device(local_rank)     # the library and torch share the CUDA runtime's current device
-        t = torch.tensor([t_ms, e2e_ms if e2e_ms is not None else 0.0], dtype=torch.float64,
-                         device=torch.device('cuda', local_rank))
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_ms, e2e_max = float(t[0]), float(t[1])
-        e2e_ms = e2e_max if e2e_ms is not None else None
-        best = {c: sc.argmax_allgather(res[c][1], res[c][0]) for c in crits}
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
-
-    peak = ctx.probe_fp64_peak()
-    ms_per_step = t_ms / args.steps
-    value = N * world / (ms_per_step * 1e-3)
-    tri = prof['tri']
-    tri_ms = tri['ms'] / max(1, tri['launches'])
-    achieved = tri['flops'] / max(tri['launches'], 1) / (tri_ms * 1e-3) / 1e12 if tri['launches'] else None
-    # with "tail_overlap" the step has TWO tri_kernel launches: the main one over complete waves (family 'tri', the
-    # dominant kernel reported here) and a small one over the head tiles ('tri_head') that runs concurrently with
-    # the evaluation kernel on a second stream -- the overlapped families' times add up to more than the step
-    tri_step_ms = tri['ms'] / args.steps
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
-        if args.config in tj and not args.candidates:
-            traffic = tj[args.config]['dram_bytes_read'] + tj[args.config]['dram_bytes_write']
-    except Exception:
-        pass
-    roofline = {'bound': 'tensor', 'kernel': 'tri_kernel (FP64 DMMA triangular contraction V = L^-1 K*)',
-                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak if achieved else None,
-                'traffic': traffic,
-                'peak_source': 'FP64 mma.sync m8n8k4 register-resident probe run in this process (MEASURED_PEAKS.json '
-                               'has no FP64 entry; cuBLAS DGEMM on this pool: 36.1 TFLOP/s, profiles/r01_fp64_peak.jsonl)',
-                'algorithmic_flops_per_launch': tri['flops'] / max(tri['launches'], 1),
-                'launch_ms': tri_ms, 'share_of_step': tri_step_ms / ms_per_step,
-                'pipeline_frac': algorithmic_flops_per_candidate(cfg) * N / (ms_per_step * 1e-3) / 1e12 / peak,
-                'kernel_ms_per_step': {k: v['ms'] / args.steps for k, v in prof.items() if v['launches']}}
-    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-            'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': dict(config, l2='flushed before every timed step (256 MiB write); panels working set >> L2',
-                           timing='CUDA events on the library stream per step, summed; max over ranks'),
-            'roofline': roofline, 'gpu_launches': launches, 'clocks': clocks,
-            'argmax': {c: int(best[c][1]) for c in crits}}
-    if e2e_ms is not None:
-        nk = len(crits)
-        line['e2e'] = {'value': N * world / (e2e_ms / args.steps * 1e-3), 'unit': UNIT,
-                       'h2d_bytes_per_step': world * N * D * 8, 'd2h_bytes_per_step': world * nk * (N * 8 + 16),
-                       'api': 'gpdoemd_b200.score_designs_multi(models, X_host_pinned, criteria, dc_out=pinned) -> dc arrays + argmax'}
-    if stepwise_ms is not None:
+            assert r_sw[c] + prob.first_row == res[c][0], 'drop-in functions and fused path disagree on the argmax'
         line['e2e_stepwise'] = {'value': N / (stepwise_ms * 1e-3), 'unit': UNIT, 'per_rank': True,
                                 'api': 'taylor_*_order(model, X) per model + HR/BH/...(mu, S, noise) per criterion, '
                                        'NumPy arrays in and out, host wall clock'}
-    if not args.no_cpu_baseline and world >= 1:
-        ns = cpu_sample_size(cfg)[args.config]
-        v, sps = cpu_reference_run(cfg, seed, ns, 1, 0)
-        line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': blas_threads(), 'kind': 'port',
-                                'sample': '%d candidates of the same workload, 1 step, NumPy/LAPACK threads = all cores' % ns}
+
+    def cpu_and_parity(cfgk, name, p, steps_cpu=1):
+        """CPU leg on a sample of p's OWN candidates (rank 0's block) + the GPU's criterion values on the same rows."""
+        ns = CPU_SAMPLE[name] if world == 1 else min(CPU_SAMPLE[name], 512)
+        res_k = p.step_e2e(None)                      # dc of every candidate of this rank's block, host side
+        must = [res_k[c][0] - p.first_row for c in p.crits]
+        idx = sample_rows(p.N, ns, must)
+        Xs = np.ascontiguousarray(p.X_host[idx])
+        adopt = (cfgk.get('inducing') or cfgk['n']) >= 2000 and not cfgk.get('inducing')
+        oms = oracle_models(cfgk, SEED, adopt_from=p.models if adopt else None)
+        v, sps, dc_cpu = cpu_leg(cfgk, oms, Xs, steps_cpu, 1 if adopt and cfgk['order'] == 2 else 0)
+        par = parity_block({c: res_k[c][2][idx] for c in p.crits}, dc_cpu, p.crits)
+        cb = {'value': v, 'unit': UNIT, 'cores': blas_threads(), 'kind': 'port',
+              'sample': '%d of this run\'s own candidates (evenly spaced + the GPU argmax rows), %d step, NumPy/LAPACK threads = %d%s'
+                        % (len(idx), steps_cpu, blas_threads(),
+                           '; posterior (alpha, L) shared with the GPU models instead of a host Cholesky per GP' +
+                           ('; GPy\'s discarded variance Jacobian skipped' if cfgk['order'] == 1 else '') if adopt else ''),
+              'parity': par}
+        return cb
+
+    if not args.no_cpu_baseline and prob.X_host is not None:
+        cb = cpu_and_parity(cfg, args.config, prob)
+        line['cpu_baseline'] = cb
+        line['parity'] = cb['parity']
+    prob.close()
+
+    if sweep is not None:
+        line['config']['scaling_sweep'] = sweep
+        line['scaling_sweep'] = sweep
+
+    # ---- C3 / C4 / C5 at a reduced N (single-GPU runs only): driver-visible roofline + parity for the big configs ------
+    if not args.no_extra and args.config == 'C2' and not args.candidates and world == 1:
+        ctx.set_scratch_bytes(64 << 30)
+        extra = {}
+        for name in ('C3', 'C4', 'C5'):
+            ck = dict(synthetic.CONFIGS[name])
+            ck['N'] = EXTRA_N[name]
+            t_setup = time.perf_counter()
+            pk = Problem(g, ctx, ck, local_rank, args.gp_build, ck['N'], 0)
+            ctx.sync()
+            t_setup = time.perf_counter() - t_setup
+            mk = measure(pk, args.extra_steps, 1, None, barrier, reduce_max)
+            msk = mk['t_ms'] / args.extra_steps
+            tr, tr_src = committed_traffic(name, ck['N'])
+            rk = roofline_of(ck, ck['N'], args.extra_steps, msk, mk['prof'], peak, tr)
+            rk['traffic_source'] = tr_src
+            entry = {'workload': workload_name(ck, name), 'value': ck['N'] / (msk * 1e-3), 'unit': UNIT, 'ms_per_step': msk,
+                     'steps': args.extra_steps, 'warmup': 1, 'gpu_launches': mk['launches'], 'roofline': rk,
+                     'e2e': {'value': ck['N'] / (mk['e2e_ms'] / args.extra_steps * 1e-3), 'unit': UNIT},
+                     'setup_s': t_setup, 'argmax': {c: int(mk['res'][c][0]) for c in pk.crits}}
+            if not args.no_cpu_baseline:
+                entry['cpu_baseline'] = cpu_and_parity(ck, name, pk)
+            pk.close()
+            extra[name] = entry
+        line['roofline']['configs'] = extra
+        line['configs'] = extra
     emit(line)
+    if scorer is not None:
+        scorer.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0

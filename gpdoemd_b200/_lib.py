@@ -12,8 +12,9 @@ LIB_PATH = os.environ.get('GPDOEMD_B200_LIB') or os.path.join(_HERE, 'libgpdoemd
 
 KERNEL_IDS = {'RBF': 0, 'Exponential': 1, 'Matern32': 2, 'Matern52': 3, 'Cosine': 4, 'RatQuad': 5}
 CRITERION_IDS = {'HR': 0, 'BH': 1, 'BF': 2, 'AW': 3, 'JR': 4}
-FAMILIES = ('eval', 'tri', 'gram', 'marginal', 'criteria', 'argmax', 'setup', 'tri_head')
+FAMILIES = ('eval', 'tri', 'gram', 'marginal', 'criteria', 'argmax', 'setup', 'tri_head', 'comm')
 NFAMILIES = len(FAMILIES)
+NCCL_ID_BYTES = 128
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -75,6 +76,14 @@ _SIGNATURES = {
     'gpd_score_multi': (C.c_int, [C.c_void_p, c_void_pp, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int, c_int32_p,
                                   C.c_int32, c_double_p, c_double_p, C.c_void_p, C.c_int32, c_double_p,
                                   C.POINTER(C.c_int64), C.c_int64]),
+    'gpd_nccl_version': (C.c_int, [c_int32_p]),
+    'gpd_nccl_unique_id': (C.c_int, [C.c_char_p]),
+    'gpd_comm_init': (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32, c_void_pp]),
+    'gpd_comm_adopt': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, c_void_pp]),
+    'gpd_comm_destroy': (None, [C.c_void_p]),
+    'gpd_score_sharded': (C.c_int, [C.c_void_p, C.c_void_p, c_void_pp, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int,
+                                    c_int32_p, C.c_int32, c_double_p, c_double_p, C.c_void_p, C.c_int32, c_double_p,
+                                    C.POINTER(C.c_int64), C.c_int64]),
     'gpd_dev_alloc': (C.c_int, [C.c_void_p, C.c_uint64, c_void_pp]),
     'gpd_dev_free': (C.c_int, [C.c_void_p, C.c_void_p]),
     'gpd_dev_upload': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -115,7 +124,12 @@ def exported_symbols():
     return sorted(_SIGNATURES)
 
 
+ERR_SINGULAR = 6
+
+
 def check(rc):
+    if rc == ERR_SINGULAR:      # the reference's np.linalg.inv raises this for a singular covariance
+        raise np.linalg.LinAlgError(load().gpd_last_error().decode('utf-8', 'replace'))
     if rc != 0:
         raise GpdError(load().gpd_last_error().decode('utf-8', 'replace'))
 

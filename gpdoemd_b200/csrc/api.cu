@@ -44,7 +44,7 @@ struct DevBuf {
     }
 };
 
-enum Family { F_EVAL = 0, F_TRI = 1, F_GRAM = 2, F_MARG = 3, F_CRIT = 4, F_ARGMAX = 5, F_SETUP = 6, F_TRI_HEAD = 7 };
+enum Family { F_EVAL = 0, F_TRI = 1, F_GRAM = 2, F_MARG = 3, F_CRIT = 4, F_ARGMAX = 5, F_SETUP = 6, F_TRI_HEAD = 7, F_COMM = 8 };
 }  // namespace gpd
 
 using namespace gpd;
@@ -607,6 +607,18 @@ static int ensure_scratch(gpd_ctx* c, size_t bytes) {
 
 static int upload_model_state(gpd_model* mo);
 
+// singular-matrix flag of the E x E inversions (kernels_crit.cu): fetched in stream order before the final
+// synchronisation of an entry point, judged after it
+static int* singular_slot(gpd_ctx* c) { return (int*)((char*)c->result_pinned + kMaxKinds * (sizeof(double) + sizeof(long long))); }
+static int singular_fetch(gpd_ctx* c) { return launch_singular_fetch(c->stream, singular_slot(c)); }
+static int singular_rc(gpd_ctx* c) {
+    if (*singular_slot(c) == 0) return 0;
+    *singular_slot(c) = 0;
+    set_error("Singular matrix (np.linalg.inv of a covariance in design_criteria.py / scipy logpdf in "
+              "discrimination_criteria.py raises LinAlgError here)");
+    return GPD_ERR_SINGULAR;
+}
+
 }  // namespace gpd
 
 // =================================================================================================
@@ -640,7 +652,7 @@ int gpd_create(int device, gpd_ctx** out) {
     GPD_CUDA(cudaMalloc(&c->best_val_dev, sizeof(double) * kMaxKinds));
     GPD_CUDA(cudaMalloc(&c->best_idx_dev, sizeof(long long) * kMaxKinds));
     GPD_CUDA(cudaMalloc(&c->argmax_partial, argmax_partial_bytes()));
-    GPD_CUDA(cudaHostAlloc(&c->result_pinned, kMaxKinds * (sizeof(double) + sizeof(long long)), cudaHostAllocDefault));
+    GPD_CUDA(cudaHostAlloc(&c->result_pinned, kMaxKinds * (sizeof(double) + sizeof(long long)) + 16, cudaHostAllocDefault));
     *out = c;
     return 0;
 }
@@ -1452,7 +1464,9 @@ int gpd_criterion(gpd_ctx* c, int kind, const double* mu, const double* S, int64
             GPD_TRY(launch_criterion(s, kind, d_mu, d_S, nc, M, E, d_noise, d_pps, d_dc, d_work));
         }
         GPD_CUDA(cudaMemcpyAsync(dc_out + start, d_dc, sizeof(double) * nc, cudaMemcpyDeviceToHost, s));
+        GPD_TRY(singular_fetch(c));
         GPD_CUDA(cudaStreamSynchronize(s));
+        GPD_TRY(singular_rc(c));
     }
     return 0;
 }
@@ -1487,7 +1501,9 @@ int gpd_gauss_loglik(gpd_ctx* c, const double* Y, const double* M, const double*
         }
         GPD_CUDA(cudaMemcpyAsync(logpdf_out + (size_t)start * N, d_l, sizeof(double) * (size_t)nc * N, cudaMemcpyDeviceToHost, s));
         GPD_CUDA(cudaMemcpyAsync(maha_out + (size_t)start * N, d_q, sizeof(double) * (size_t)nc * N, cudaMemcpyDeviceToHost, s));
+        GPD_TRY(singular_fetch(c));
         GPD_CUDA(cudaStreamSynchronize(s));
+        GPD_TRY(singular_rc(c));
     }
     return 0;
 }
@@ -1519,7 +1535,7 @@ int gpd_argmax(gpd_ctx* c, const double* dc, int64_t N, double* best_val, int64_
 // =================================================================================================
 static int score_impl(gpd_ctx* c, gpd_model* const* models, int32_t M, const double* X, bool x_on_device, int64_t N,
                       int order, const int32_t* kinds, int nk, const double* noise, const double* pps, double* dc_out,
-                      bool dc_on_device, double* best_val, int64_t* best_idx, int64_t idx_offset) {
+                      bool dc_on_device, double* best_val, int64_t* best_idx, int64_t idx_offset, bool finish = true) {
     GPD_CHECK(c && models && X && noise && pps && kinds, "null argument");
     GPD_CHECK(N >= 1, "no candidates");
     GPD_CHECK(M >= 1 && M <= 64, "number of models out of range (1..64)");
@@ -1636,11 +1652,14 @@ static int score_impl(gpd_ctx* c, gpd_model* const* models, int32_t M, const dou
             for (int k = 0; k < nk; ++k)
                 GPD_CUDA(cudaMemcpyAsync(dc_out + (size_t)k * N + start, dcp[k], sizeof(double) * nc, cudaMemcpyDeviceToHost, s));
     }
+    if (!finish) return 0;      // gpd_score_sharded: the running best stays on the device for the all-gather
     double* bv = (double*)c->result_pinned;
     long long* bi = (long long*)(bv + kMaxKinds);
     GPD_CUDA(cudaMemcpyAsync(bv, c->best_val_dev, sizeof(double) * nk, cudaMemcpyDeviceToHost, s));
     GPD_CUDA(cudaMemcpyAsync(bi, c->best_idx_dev, sizeof(long long) * nk, cudaMemcpyDeviceToHost, s));
+    GPD_TRY(singular_fetch(c));
     GPD_CUDA(cudaStreamSynchronize(s));
+    GPD_TRY(singular_rc(c));
     for (int k = 0; k < nk; ++k) {
         if (best_val) best_val[k] = bv[k];
         if (best_idx) best_idx[k] = bi[k];
@@ -1665,6 +1684,192 @@ int gpd_score_multi(gpd_ctx* c, gpd_model* const* models, int32_t M, const doubl
                     double* dc_out, int32_t dc_on_device, double* best_val, int64_t* best_idx, int64_t idx_offset) {
     return score_impl(c, models, M, X, x_on_device != 0, N, order, kinds, nkinds, noise, pps, dc_out, dc_on_device != 0,
                       best_val, best_idx, idx_offset);
+}
+
+// =================================================================================================
+// multi-GPU: candidates sharded, GP state replicated, ONE collective per scoring call
+// =================================================================================================
+}  // extern "C"
+
+#include <dlfcn.h>
+#include <nccl.h>      // types and prototypes only: the library is bound at run time (no link dependency)
+
+namespace gpd {
+// NCCL is resolved with dlopen so that libgpdoemd_b200.so loads on a machine without NCCL; the sharded entry
+// points then fail loudly.  If the process already holds a libnccl.so.2 (e.g. the one bundled with PyTorch) that
+// instance is reused, so both sides talk to one NCCL.
+struct NcclApi {
+    void* handle = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&ncclGetVersion) GetVersion = nullptr;
+};
+static NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.handle ? &api : nullptr;
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return nullptr;
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+    api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+    api.GetVersion = (decltype(api.GetVersion))dlsym(h, "ncclGetVersion");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.GetErrorString) return nullptr;
+    api.handle = h;
+    return &api;
+}
+#define GPD_NCCL(api, call)                                                                            \
+    do {                                                                                               \
+        ncclResult_t r__ = (call);                                                                     \
+        if (r__ != ncclSuccess) {                                                                      \
+            ::gpd::set_error(std::string(#call) + ": " + (api)->GetErrorString(r__));                  \
+            return 5;                                                                                  \
+        }                                                                                              \
+    } while (0)
+}  // namespace gpd
+
+struct gpd_comm {
+    gpd_ctx* ctx = nullptr;
+    ncclComm_t comm = nullptr;
+    bool owned = false;             // created by gpd_comm_init (destroyed with the handle) or adopted from the caller
+    int rank = 0, world = 1;
+    void *send_dev = nullptr, *recv_dev = nullptr;     // Best[kMaxKinds], Best[world][kMaxKinds]
+};
+
+extern "C" {
+
+int gpd_nccl_version(int32_t* version_out) {
+    GPD_CHECK(version_out, "null argument");
+    NcclApi* api = nccl_api();
+    GPD_CHECK(api, "libnccl.so.2 cannot be loaded: the sharded entry points need NCCL (there is no fallback)");
+    int v = 0;
+    if (api->GetVersion) GPD_NCCL(api, api->GetVersion(&v));
+    *version_out = v;
+    return 0;
+}
+
+int gpd_nccl_unique_id(char id_out[GPD_NCCL_ID_BYTES]) {
+    GPD_CHECK(id_out, "null argument");
+    static_assert(sizeof(ncclUniqueId) == GPD_NCCL_ID_BYTES, "ncclUniqueId is 128 bytes");
+    NcclApi* api = nccl_api();
+    GPD_CHECK(api, "libnccl.so.2 cannot be loaded: the sharded entry points need NCCL (there is no fallback)");
+    ncclUniqueId id;
+    GPD_NCCL(api, api->GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof(id));
+    return 0;
+}
+
+static int comm_alloc(gpd_ctx* c, gpd_comm* cm) {
+    GPD_CUDA(cudaMalloc(&cm->send_dev, best_pair_bytes() * kMaxKinds));
+    GPD_CUDA(cudaMalloc(&cm->recv_dev, best_pair_bytes() * kMaxKinds * (size_t)cm->world));
+    (void)c;
+    return 0;
+}
+
+int gpd_comm_init(gpd_ctx* c, const char id[GPD_NCCL_ID_BYTES], int32_t rank, int32_t world, gpd_comm** out) {
+    GPD_CHECK(c && id && out, "null argument");
+    *out = nullptr;
+    GPD_CHECK(world >= 1 && rank >= 0 && rank < world, "bad rank / world size");
+    NcclApi* api = nccl_api();
+    GPD_CHECK(api, "libnccl.so.2 cannot be loaded: the sharded entry points need NCCL (there is no fallback)");
+    GPD_CUDA(cudaSetDevice(c->device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    gpd_comm* cm = new gpd_comm();
+    cm->ctx = c;
+    cm->rank = rank;
+    cm->world = world;
+    cm->owned = true;
+    ncclResult_t r = api->CommInitRank(&cm->comm, world, uid, rank);
+    if (r != ncclSuccess) {
+        set_error(std::string("ncclCommInitRank: ") + api->GetErrorString(r));
+        delete cm;
+        return 5;
+    }
+    if (int rc = comm_alloc(c, cm)) {
+        gpd_comm_destroy(cm);
+        return rc;
+    }
+    *out = cm;
+    return 0;
+}
+
+int gpd_comm_adopt(gpd_ctx* c, void* nccl_comm, int32_t rank, int32_t world, gpd_comm** out) {
+    GPD_CHECK(c && nccl_comm && out, "null argument");
+    *out = nullptr;
+    GPD_CHECK(world >= 1 && rank >= 0 && rank < world, "bad rank / world size");
+    GPD_CHECK(nccl_api(), "libnccl.so.2 cannot be loaded: the sharded entry points need NCCL (there is no fallback)");
+    GPD_CUDA(cudaSetDevice(c->device));
+    gpd_comm* cm = new gpd_comm();
+    cm->ctx = c;
+    cm->comm = (ncclComm_t)nccl_comm;
+    cm->rank = rank;
+    cm->world = world;
+    if (int rc = comm_alloc(c, cm)) {
+        gpd_comm_destroy(cm);
+        return rc;
+    }
+    *out = cm;
+    return 0;
+}
+
+void gpd_comm_destroy(gpd_comm* cm) {
+    if (!cm) return;
+    cudaSetDevice(cm->ctx->device);
+    cudaStreamSynchronize(cm->ctx->stream);
+    NcclApi* api = nccl_api();
+    if (cm->owned && cm->comm && api) api->CommDestroy(cm->comm);
+    cudaFree(cm->send_dev);
+    cudaFree(cm->recv_dev);
+    delete cm;
+}
+
+// The data-parallel step of SURVEY 8(e) / BASELINE configs[4]: this rank scores ITS contiguous block of the candidates
+// (N_local rows starting at global index idx_offset; N_local may be 0) exactly like gpd_score_multi, then the nkinds
+// (max, global index) pairs of all ranks are all-gathered on the library stream (world x nkinds x 16 bytes, the only
+// collective) and folded on the device with np.argmax semantics.  best_val / best_idx are the GLOBAL winners and are
+// identical on every rank.
+int gpd_score_sharded(gpd_ctx* c, gpd_comm* cm, gpd_model* const* models, int32_t M, const double* X, int32_t x_on_device,
+                      int64_t N_local, int order, const int32_t* kinds, int32_t nkinds, const double* noise,
+                      const double* pps, double* dc_out, int32_t dc_on_device, double* best_val, int64_t* best_idx,
+                      int64_t idx_offset) {
+    GPD_CHECK(c && cm && cm->ctx == c, "communicator does not belong to this context");
+    GPD_CHECK(N_local >= 0, "negative shard size");
+    GPD_CHECK(nkinds >= 1 && nkinds <= kMaxKinds, "1..5 criteria per call");
+    NcclApi* api = nccl_api();
+    GPD_CHECK(api, "libnccl.so.2 cannot be loaded");
+    GPD_CUDA(cudaSetDevice(c->device));
+    if (N_local > 0)
+        GPD_TRY(score_impl(c, models, M, X, x_on_device != 0, N_local, order, kinds, nkinds, noise, pps, dc_out,
+                           dc_on_device != 0, nullptr, nullptr, idx_offset, false));
+    cudaStream_t s = c->stream;
+    const size_t bytes = best_pair_bytes() * (size_t)nkinds;
+    {
+        Span sp(c, F_COMM, 2, 0);
+        GPD_TRY(launch_best_pack(s, c->best_val_dev, c->best_idx_dev, nkinds, N_local == 0, cm->send_dev));
+        GPD_NCCL(api, api->AllGather(cm->send_dev, cm->recv_dev, bytes, ncclUint8, cm->comm, s));
+        GPD_TRY(launch_best_reduce(s, cm->recv_dev, cm->world, nkinds, c->best_val_dev, c->best_idx_dev));
+    }
+    double* bv = (double*)c->result_pinned;
+    long long* bi = (long long*)(bv + kMaxKinds);
+    GPD_CUDA(cudaMemcpyAsync(bv, c->best_val_dev, sizeof(double) * nkinds, cudaMemcpyDeviceToHost, s));
+    GPD_CUDA(cudaMemcpyAsync(bi, c->best_idx_dev, sizeof(long long) * nkinds, cudaMemcpyDeviceToHost, s));
+    GPD_TRY(singular_fetch(c));
+    GPD_CUDA(cudaStreamSynchronize(s));
+    GPD_TRY(singular_rc(c));
+    for (int k = 0; k < nkinds; ++k) {
+        if (best_val) best_val[k] = bv[k];
+        if (best_idx) best_idx[k] = bi[k];
+    }
+    return 0;
 }
 
 // ---- layout self-description --------------------------------------------------------------------

@@ -138,6 +138,10 @@ int launch_gauss_loglik(cudaStream_t s, const double* Y, const double* Mu, const
 int launch_argmax(cudaStream_t s, const double* dc, long long N, long long idx_base, double* best_val_dev,
                   long long* best_idx_dev, int first, void* partial_dev);
 size_t argmax_partial_bytes();
+size_t best_pair_bytes();
+int launch_singular_fetch(cudaStream_t s, int* host_out);
+int launch_best_pack(cudaStream_t s, const double* bv, const long long* bi, int nk, int empty, void* out);
+int launch_best_reduce(cudaStream_t s, const void* all, int world, int nk, double* bv, long long* bi);
 size_t crit_partial_bytes(int N, int nk);
 int launch_post1(cudaStream_t s, const PostModel* pms_dev, const RawOut* raws_dev, int M, int E, int N, int chunk_n,
                  const double* noise_dev, double* work, const int* kinds, int nk);

@@ -185,6 +185,11 @@ int launch_assemble(cudaStream_t s, int order, int N, int E, int P, double* mu, 
 // ---------------------------------------------------------------------------------------------
 // register-resident E x E inverse + determinant (Gauss-Jordan, partial pivoting like LAPACK getrf)
 // ---------------------------------------------------------------------------------------------
+// An exactly zero pivot = a singular matrix: np.linalg.inv (design_criteria.py:83,115,137,173) raises LinAlgError there.
+// The kernels cannot raise, so they set this per-device flag; the host entry points read and reset it at their final
+// synchronisation and return GPD_ERR_SINGULAR.  (All writers store 1: the race is benign.)
+__device__ int g_singular_flag = 0;
+
 template <int E>
 __device__ __forceinline__ double inv_inplace(double (&A)[E][E]) {
     int piv[E];
@@ -207,6 +212,7 @@ __device__ __forceinline__ double inv_inplace(double (&A)[E][E]) {
                 det = -det;
             }
         const double d = A[c][c];
+        if (d == 0.0) g_singular_flag = 1;
         det *= d;
         const double id = 1.0 / d;
         A[c][c] = 1.0;
@@ -757,6 +763,48 @@ int launch_argmax(cudaStream_t s, const double* dc, long long N, long long idx_b
     argmax_stage1<<<blocks, 256, 0, s>>>(dc, N, idx_base, (Best*)partial_dev);
     GPD_CUDA(cudaGetLastError());
     argmax_stage2<<<1, 256, 0, s>>>((const Best*)partial_dev, blocks, first, best_val_dev, best_idx_dev);
+    GPD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sharded scoring (gpd_score_sharded): every rank packs its running (max, index) pairs, one ncclAllGather moves
+// world x nk x 16 bytes, and every rank folds the gathered pairs with np.argmax semantics (NaN wins, ties go to
+// the lowest global index; an empty shard publishes index -1 and never wins)
+// ---------------------------------------------------------------------------------------------
+__global__ void best_pack_kernel(const double* __restrict__ bv, const long long* __restrict__ bi, int nk, int empty,
+                                 Best* __restrict__ out) {
+    const int k = threadIdx.x;
+    if (k < nk) out[k] = empty ? Best{0.0, -1} : Best{bv[k], bi[k]};
+}
+__global__ void best_reduce_kernel(const Best* __restrict__ all, int world, int nk, double* __restrict__ bv,
+                                   long long* __restrict__ bi) {
+    const int k = threadIdx.x;
+    if (k >= nk) return;
+    Best x{0.0, -1};
+    for (int r = 0; r < world; ++r) {
+        const Best p = all[(size_t)r * nk + k];
+        if (p.i >= 0 && (x.i < 0 || better(p.v, p.i, x.v, x.i))) x = p;
+    }
+    bv[k] = x.v;
+    bi[k] = x.i;
+}
+size_t best_pair_bytes() { return sizeof(Best); }
+// copy the singular-matrix flag to (pinned) host memory and clear it, in stream order
+int launch_singular_fetch(cudaStream_t s, int* host_out) {
+    int* flag_dev = nullptr;
+    GPD_CUDA(cudaGetSymbolAddress((void**)&flag_dev, g_singular_flag));
+    GPD_CUDA(cudaMemcpyAsync(host_out, flag_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+    GPD_CUDA(cudaMemsetAsync(flag_dev, 0, sizeof(int), s));
+    return 0;
+}
+int launch_best_pack(cudaStream_t s, const double* bv, const long long* bi, int nk, int empty, void* out) {
+    best_pack_kernel<<<1, 32, 0, s>>>(bv, bi, nk, empty, (Best*)out);
+    GPD_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_best_reduce(cudaStream_t s, const void* all, int world, int nk, double* bv, long long* bi) {
+    best_reduce_kernel<<<1, 32, 0, s>>>((const Best*)all, world, nk, bv, bi);
     GPD_CUDA(cudaGetLastError());
     return 0;
 }

@@ -36,7 +36,10 @@ __global__ void pstate_kernel(int kernel, int n, int n_pad, int P, int dim_z, co
         double ls = ls_p[a];
         d[a] = pstar[a] - Zp[(size_t)i * dim_z + a];
         l2[a] = ls * ls;
-        double s = pstar[a] / ls - Zp[(size_t)i * dim_z + a] / ls;   // GPy scales each argument first
+        // difference first, then the scaling: when p* comes within 1e-5 of a training parameter the 1/r terms of
+        // the second derivative (Exponential: kappa has a cusp at r = 0) need r to full relative accuracy; scaling
+        // each argument first (GPy) or GPy's expanded-form distance lose u / r there (tests/test_d2mu_truth.py)
+        double s = d[a] / ls;
         r2 += s * s;
     }
     double r = sqrt(r2);

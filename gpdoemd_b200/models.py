@@ -83,6 +83,7 @@ class GPModel:
         self.binary_variables = model_dict.get('binary_variables', [])
         self.gp_noise_var = model_dict.get('gp_noise_var', 1e-6)
         self._device = device
+        self._dev_ctx = None          # Context the device handles live in
         self._dev_model = None        # gpd_model*
         self._dev_gps = []            # gpd_gp* handles
         self._dev_pstar = None
@@ -238,10 +239,12 @@ class GPModel:
             self.trans_x = BoxTransform(self.xmin, self.xmax)
             self.trans_p = BoxTransform(self.pmin, self.pmax)
             self._Z = self.trans_z(value)
+            self._invalidate_device()      # the device model holds xmin/xmax/pmin/pmax
 
     @Z.deleter
     def Z(self):
         self._Z = None
+        self._invalidate_device()
 
     zmin = property(lambda self: self._zmin)
     zmax = property(lambda self: self._zmax)
@@ -271,10 +274,12 @@ class GPModel:
             self._ystd = np.std(value, axis=0)
             self.trans_y = MeanTransform(self.ymean, self.ystd)
             self._Y = self.trans_y(value)
+            self._invalidate_device()      # the device model holds ymean/ystd
 
     @Y.deleter
     def Y(self):
         self._Y = None
+        self._invalidate_device()
 
     ymean = property(lambda self: self._ymean)
     ystd = property(lambda self: self._ystd)
@@ -426,10 +431,14 @@ class GPModel:
         self._cache = None
         if getattr(self, '_dev_model', None) is None:
             return
-        ctx = get_context(self._device)
-        ctx.lib.gpd_model_free(self._dev_model)
-        for h in self._dev_gps:
-            ctx.lib.gpd_gp_free(h)
+        # the context the handles were created in; after Context.close() (gpd_destroy) its handles are gone with it
+        # and must not be touched (gpd_model_free would dereference the deleted context)
+        ctx = getattr(self, '_dev_ctx', None)
+        if ctx is not None and ctx.handle:
+            ctx.lib.gpd_model_free(self._dev_model)
+            for h in self._dev_gps:
+                ctx.lib.gpd_gp_free(h)
+        self._dev_ctx = None
         self._dev_model, self._dev_gps = None, []
         self._dev_pstar = self._dev_sigma = None
         self._dev_key = None
@@ -442,9 +451,11 @@ class GPModel:
 
     def _ensure_device(self):
         if self._dev_model is not None:
-            return
+            if self._dev_ctx.handle:
+                return
+            self._invalidate_device()          # the context was closed: rebuild in a fresh one
         assert self.gps is not None, 'no GP surrogate: call gp_surrogate() (and gp_load_hyp()) first'
-        ctx = get_context(self._device)
+        ctx = self._dev_ctx = get_context(self._device)
         E, R = self.num_outputs, 2 ** self.dim_b
         handles = (C.c_void_p * (E * R))()
         for e in range(E):
@@ -482,13 +493,18 @@ class GPModel:
             key = (self.pmean.tobytes(), None if self.Sigma is None else self.Sigma.tobytes())
             if key == getattr(self, '_dev_key', None):
                 return
-        ctx = get_context(self._device)
         key_after = None
         if pstar is None:
             pstar = self.trans_p(self.pmean)
             key_after = key
         pstar = _lib.as_f64(pstar)
         sig = None if self.Sigma is None else _lib.as_f64(self.Sigma)
+        if sig is None and self._dev_sigma is not None:
+            # `del model.Sigma` / `model.Sigma = None` after an upload: the device copy must not survive
+            # (taylor_first_order.py:38 would fail on model.Sigma = None)
+            self._invalidate_device()
+            self._ensure_device()
+        ctx = self._dev_ctx
         same_p = self._dev_pstar is not None and np.array_equal(self._dev_pstar, pstar)
         same_s = (sig is None) or (self._dev_sigma is not None and np.array_equal(self._dev_sigma, sig))
         if same_p and same_s:
@@ -506,8 +522,15 @@ class GPModel:
 
     def device_handle(self):
         """gpd_model* with pmean/Sigma synchronised (used by the fused scoring path)."""
+        assert self.Sigma is not None, 'model.Sigma is not set (taylor_first_order.py:38 reads it)'
         self._sync_device()
         return self._dev_model
+
+    def replicate(self, device):
+        """The same trained model bound to another GPU (GP state replicated: SURVEY 8e); host arrays are shared."""
+        m = type(self).from_reference(self, device=device)
+        m.build_on_device = self.build_on_device
+        return m
 
     # ---- hooks (transformed units) = the device boundary ---------------------------------------
     _FLAG_KEYS = ('dmu', 'd2mu', 'ds2', 'd2s2')
@@ -532,7 +555,7 @@ class GPModel:
         assert Xt.ndim == 2 and Xt.shape[1] == self.dim_x
         self.check_routing(Xt)
         self._sync_device(pstar)
-        key = (Xt.shape, hash(Xt.tobytes()), self._dev_pstar.tobytes())
+        key = (Xt.shape, Xt.tobytes(), self._dev_pstar.tobytes())      # compared by content, not by hash
         c = self._cache
         if c is not None and c['key'] == key and all(k in c for k in want):
             return c
@@ -544,7 +567,7 @@ class GPModel:
         for k in self._FLAG_KEYS:
             if k in want:
                 out[k] = np.empty(shapes[k])
-        ctx = get_context(self._device)
+        ctx = self._dev_ctx
         check(ctx.lib.gpd_hooks(self._dev_model, dptr(Xt), N, 1, dptr(out['mu']), dptr(out['s2']),
                                 dptr(out.get('dmu')), dptr(out.get('d2mu')), dptr(out.get('ds2')),
                                 dptr(out.get('d2s2'))))

@@ -46,8 +46,12 @@ def _prep(models, criterion, noise_var, pps):
 
 
 def score_designs_multi(models, X, criteria, order=1, noise_var=None, pps=None, return_dc=True, idx_offset=0,
-                        x_dev=None, N=None, dc_dev=None, dc_out=None):
+                        x_dev=None, N=None, dc_dev=None, dc_out=None, comm=None):
     """Several criteria in one pass over the candidates -> {name: (best_index, best_value, dc or None)}.
+
+    ``comm`` (a ``LibraryComm``): X / x_dev is THIS rank's contiguous block of a sharded candidate set (it may be
+    empty) starting at global index ``idx_offset``; the call then goes through ``gpd_score_sharded`` and the returned
+    best index / value are the global winners after the all-gather (identical on every rank).
 
     X is a host (N, dim_x) array, or pass ``x_dev`` (device pointer) and ``N`` for resident candidates
     (then ``dc_dev`` may be a device pointer to [len(criteria)][N] doubles).  ``dc_out``: optional preallocated
@@ -77,9 +81,15 @@ def score_designs_multi(models, X, criteria, order=1, noise_var=None, pps=None, 
         dc = None
         xp, x_on_dev = x_dev, 1
         dcp, dc_on_dev = dc_dev, 1
-    check(ctx.lib.gpd_score_multi(ctx.handle, C.cast(handles, _lib.c_void_pp), len(models), xp, x_on_dev, int(N), order,
-                                  kinds.ctypes.data_as(_lib.c_int32_p), nk, dptr(noise), dptr(pps_n), dcp, dc_on_dev,
-                                  dptr(bv), bi, int(idx_offset)))
+    if comm is not None:
+        assert comm.ctx is ctx, 'communicator and models live on different devices'
+        check(ctx.lib.gpd_score_sharded(ctx.handle, comm.handle, C.cast(handles, _lib.c_void_pp), len(models), xp, x_on_dev,
+                                        int(N), order, kinds.ctypes.data_as(_lib.c_int32_p), nk, dptr(noise), dptr(pps_n),
+                                        dcp, dc_on_dev, dptr(bv), bi, int(idx_offset)))
+    else:
+        check(ctx.lib.gpd_score_multi(ctx.handle, C.cast(handles, _lib.c_void_pp), len(models), xp, x_on_dev, int(N), order,
+                                      kinds.ctypes.data_as(_lib.c_int32_p), nk, dptr(noise), dptr(pps_n), dcp, dc_on_dev,
+                                      dptr(bv), bi, int(idx_offset)))
     return {c: (int(bi[k]), float(bv[k]), None if dc is None else dc[k]) for k, c in enumerate(criteria)}
 
 
@@ -193,35 +203,97 @@ def combine_best(vals, idxs):
     return best
 
 
-class ShardedScorer:
-    """Data-parallel scoring over a torch.distributed group (NCCL on GPUs, gloo in CPU tests).
+class LibraryComm:
+    """One NCCL communicator owned by the C library and bound to a device context (``gpd_comm_init``).  ``unique_id()``
+    on one rank, the 128 bytes to every rank over any channel, then ``LibraryComm(ctx, uid, rank, world)`` on all of
+    them concurrently (threads of one process or one process per GPU)."""
 
-    ``local_score(lo, hi) -> (best_value, best_global_index)`` is the per-rank work; the only
-    collective is an all-gather of one (float64, int64) pair per rank.
+    def __init__(self, ctx, uid, rank, world):
+        assert len(uid) == _lib.NCCL_ID_BYTES
+        self.ctx, self.rank, self.world = ctx, int(rank), int(world)
+        h = C.c_void_p()
+        check(ctx.lib.gpd_comm_init(ctx.handle, bytes(uid), self.rank, self.world, C.byref(h)))
+        self.handle = h
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(_lib.NCCL_ID_BYTES)
+        check(_lib.load().gpd_nccl_unique_id(buf))
+        return buf.raw
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.gpd_comm_destroy(self.handle)
+            self.handle = None
+
+
+def pack_best(vals, idxs):
+    """(float64 value, int64 index) pairs as ONE int64 vector [bits(v0), i0, bits(v1), i1, ...] (one collective)."""
+    out = np.empty(2 * len(vals), dtype=np.int64)
+    out[0::2] = np.asarray(vals, dtype=np.float64).view(np.int64)
+    out[1::2] = np.asarray(idxs, dtype=np.int64)
+    return out
+
+
+def unpack_best(packed):
+    packed = np.ascontiguousarray(packed, dtype=np.int64)
+    return packed[0::2].view(np.float64).copy(), packed[1::2].copy()
+
+
+class ShardedScorer:
+    """Data-parallel scoring over a torch.distributed group: one process per GPU, candidates in contiguous blocks,
+    GP factors replicated.  The only collective is ONE all-gather of the per-rank (float64 best value, int64 best
+    global index) pairs of all criteria:
+
+    * NCCL groups: the C library owns a communicator of its own (bootstrapped over the torch group) and
+      ``score_designs_multi`` runs ``gpd_score_sharded`` -- scoring, ncclAllGather and the np.argmax fold are
+      enqueued on the library stream, one host synchronisation per call;
+    * other backends (gloo in the CPU tests): ``argmax_allgather`` packs the pairs into one int64 tensor.
     """
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, device=None):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        self.backend = dist.get_backend(group)
+        self.device = default_device() if device is None else int(device)
+        self.comm = None
+        if self.backend == 'nccl':
+            import torch
+            ctx = get_context(self.device)
+            dev = torch.device('cuda', self.device)
+            uid = LibraryComm.unique_id() if self.rank == 0 else bytes(_lib.NCCL_ID_BYTES)
+            t = torch.frombuffer(bytearray(uid), dtype=torch.uint8).to(dev)
+            dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            self.comm = LibraryComm(ctx, bytes(t.cpu().numpy().tobytes()), self.rank, self.world)
+
+    def close(self):
+        if self.comm is not None:
+            self.comm.close()
+            self.comm = None
+
+    def score_designs_multi(self, models, X_local, criteria, idx_offset, **kw):
+        """This rank's block through the fused scorer + the in-stream all-gather -> global winners per criterion."""
+        assert self.comm is not None, 'gpd_score_sharded needs an NCCL process group (GPU ranks)'
+        return score_designs_multi(models, X_local, criteria, idx_offset=idx_offset, comm=self.comm, **kw)
 
     def argmax_allgather(self, best_val, best_idx, device=None):
+        """Fold per-rank winners of one or several criteria: scalars -> (value, index); sequences -> list of pairs."""
         import torch
-        dist = self.dist
-        backend = dist.get_backend(self.group)
-        # the rank's own GPU, not "current device": the library and torch share the CUDA runtime's current device
-        dev = device if device is not None else ('cuda:%d' % default_device() if backend == 'nccl' else 'cpu')
-        v = torch.tensor([best_val], dtype=torch.float64, device=dev)
-        i = torch.tensor([best_idx], dtype=torch.int64, device=dev)
-        vs = [torch.empty_like(v) for _ in range(self.world)]
-        is_ = [torch.empty_like(i) for _ in range(self.world)]
-        dist.all_gather(vs, v, group=self.group)
-        dist.all_gather(is_, i, group=self.group)
-        vals = [float(t.item()) for t in vs]
-        idxs = [int(t.item()) for t in is_]
-        return combine_best(vals, idxs)
+        scalar = np.ndim(best_val) == 0
+        vals, idxs = np.atleast_1d(best_val), np.atleast_1d(best_idx)
+        dev = device if device is not None else ('cuda:%d' % self.device if self.backend == 'nccl' else 'cpu')
+        mine = torch.from_numpy(pack_best(vals, idxs)).to(dev)
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(gathered, mine, group=self.group)
+        allp = torch.stack(gathered).cpu().numpy()                  # (world, 2 nk): one device -> host copy
+        out = []
+        for k in range(len(vals)):
+            v, i = unpack_best(allp[:, 2 * k:2 * k + 2].ravel())
+            out.append(combine_best(v.tolist(), i.tolist()))
+        return out[0] if scalar else out
 
     def score(self, N, local_score):
         lo, hi = shard_bounds(N, self.rank, self.world)
@@ -230,3 +302,49 @@ class ShardedScorer:
         else:
             v, i = 0.0, -1
         return self.argmax_allgather(v, i)
+
+
+class MultiDeviceScorer:
+    """The reference's single-process design loop (demos/case_study.py:279-293) over SEVERAL GPUs of one box: one
+    context, one replica of every model's GP state and one host thread per device; candidates are cut into contiguous
+    blocks, each thread runs ``gpd_score_sharded`` on its block, and the NCCL all-gather inside that call makes every
+    thread return the global winners (ties -> lowest global index, like ``np.argmax`` on the whole grid)."""
+
+    def __init__(self, models, devices):
+        from concurrent.futures import ThreadPoolExecutor
+        self.devices = [int(d) for d in devices]
+        assert len(self.devices) >= 1 and len(set(self.devices)) == len(self.devices)
+        self.models = list(models)
+        W = len(self.devices)
+        self.pool = ThreadPoolExecutor(W)
+        self.replicas = [[m if m._device == d else m.replicate(d) for m in self.models] for d in self.devices]
+        uid = LibraryComm.unique_id()
+        # ncclCommInitRank is collective: every rank's thread must be inside it at the same time
+        self.comms = list(self.pool.map(lambda r: LibraryComm(get_context(self.devices[r]), uid, r, W), range(W)))
+
+    def close(self):
+        for c in self.comms:
+            c.close()
+        self.comms = []
+        self.pool.shutdown()
+
+    def score_designs_multi(self, X, criteria, order=1, noise_var=None, pps=None, return_dc=True):
+        """-> {name: (best_index, best_value, dc or None)} over the whole X (host array, original units)."""
+        X = _lib.as_f64(X)
+        N, W = len(X), len(self.devices)
+        for reps in self.replicas:                       # pmean / Sigma follow the caller's models
+            for src, rep in zip(self.models, reps):
+                if rep is not src:
+                    rep.pmean, rep.Sigma = src.pmean, src.Sigma
+
+        def work(r):
+            lo, hi = shard_bounds(N, r, W)
+            return score_designs_multi(self.replicas[r], X[lo:hi], criteria, order=order, noise_var=noise_var, pps=pps,
+                                       return_dc=return_dc, idx_offset=lo, comm=self.comms[r])
+        parts = list(self.pool.map(work, range(W)))
+        out = {}
+        for c in criteria:
+            assert all(p[c][0] == parts[0][c][0] for p in parts), 'ranks disagree on the global argmax'
+            dc = np.concatenate([p[c][2] for p in parts]) if return_dc else None
+            out[c] = (parts[0][c][0], parts[0][c][1], dc)
+        return out

@@ -30,6 +30,7 @@ extern "C" {
 typedef struct gpd_ctx gpd_ctx;
 typedef struct gpd_gp gpd_gp;
 typedef struct gpd_model gpd_model;
+typedef struct gpd_comm gpd_comm;   /* one NCCL communicator bound to a context (multi-GPU scoring) */
 
 /* GPdoemd/kernels/stationary.py:33-99 -- the six ARD stationary kernels */
 enum gpd_kernel {
@@ -74,6 +75,11 @@ typedef struct gpd_gp_desc {
 } gpd_gp_desc;
 enum gpd_factor_kind { GPD_FACTOR_CHOL = 0, GPD_FACTOR_ROOT = 1 };
 
+/* return codes: 0 ok; 1 CUDA error; 2 invalid argument; 3 unsupported size; 4 covariance not positive definite
+ * (gpd_gp_build); 5 NCCL error; GPD_ERR_SINGULAR: an E x E covariance handed to a criterion was exactly singular
+ * (np.linalg.inv in design_criteria.py:83,115,137,173 raises numpy.linalg.LinAlgError there) */
+enum { GPD_ERR_SINGULAR = 6 };
+
 /* ---- context ----------------------------------------------------------------------------- */
 int  gpd_create(int device, gpd_ctx** out);
 void gpd_destroy(gpd_ctx* ctx);
@@ -93,8 +99,9 @@ uint64_t gpd_launch_count(gpd_ctx* ctx);
  * enable, run, then read the accumulated milliseconds / launch counts.  family index:
  * 0 eval (kernel+derivative rows), 1 tri (DMMA triangular contraction), 2 gram, 3 marginal,
  * 4 criteria, 5 argmax, 6 setup (p-state, routing, packing), 7 tri_head (the small triangular launch over the
- * head tiles that runs concurrently with the evaluation of the remaining tiles, option "tail_overlap") */
-enum { GPD_NFAMILIES = 8 };
+ * head tiles that runs concurrently with the evaluation of the remaining tiles, option "tail_overlap"),
+ * 8 comm (pack + ncclAllGather + fold of the per-rank (max, index) pairs in gpd_score_sharded) */
+enum { GPD_NFAMILIES = 9 };
 int  gpd_profile_enable(gpd_ctx* ctx, int on);
 int  gpd_profile_read(gpd_ctx* ctx, double ms_out[GPD_NFAMILIES], uint64_t launches_out[GPD_NFAMILIES],
                       double flops_out[GPD_NFAMILIES]);
@@ -203,6 +210,28 @@ int  gpd_score_multi(gpd_ctx* ctx, gpd_model* const* models, int32_t M, const do
                      int64_t N, int order, const int32_t* kinds, int32_t nkinds, const double* noise,
                      const double* pps, double* dc_out, int32_t dc_on_device, double* best_val,
                      int64_t* best_idx, int64_t idx_offset);
+/* ---- multi-GPU (BASELINE configs[4]): candidates sharded in contiguous blocks, GP state replicated,
+ * ONE collective per scoring call = the all-gather of the per-rank (best value, best global index) pairs.  The
+ * reference is single-process (demos/case_study.py:279-293 takes np.argmax over the whole grid); these entry points
+ * are what a maintainer binds to spread that grid over the GPUs of a box -- one context (and one host thread or one
+ * process) per GPU.  NCCL is resolved at run time (dlopen of libnccl.so.2; an instance already loaded by the process,
+ * e.g. PyTorch's, is reused); without it these calls fail, there is no fallback. */
+enum { GPD_NCCL_ID_BYTES = 128 };          /* sizeof(ncclUniqueId) */
+int  gpd_nccl_version(int32_t* version_out);
+/* ncclGetUniqueId: call on ONE rank, hand the 128 bytes to the others (any channel: torch.distributed, MPI, a file) */
+int  gpd_nccl_unique_id(char id_out[GPD_NCCL_ID_BYTES]);
+/* ncclCommInitRank on the context's device; collective over the `world` ranks (threads or processes) */
+int  gpd_comm_init(gpd_ctx* ctx, const char id[GPD_NCCL_ID_BYTES], int32_t rank, int32_t world, gpd_comm** out);
+/* wrap an ncclComm_t the caller already owns (not destroyed by gpd_comm_destroy) */
+int  gpd_comm_adopt(gpd_ctx* ctx, void* nccl_comm /* ncclComm_t */, int32_t rank, int32_t world, gpd_comm** out);
+void gpd_comm_destroy(gpd_comm* comm);
+/* gpd_score_multi on this rank's block [idx_offset, idx_offset + N_local) (N_local may be 0), then the all-gather and
+ * the np.argmax fold (NaN wins, ties -> lowest global index) on the library stream; best_val / best_idx (nkinds
+ * entries) are the GLOBAL winners, identical on every rank.  dc_out (may be NULL) receives this rank's block only. */
+int  gpd_score_sharded(gpd_ctx* ctx, gpd_comm* comm, gpd_model* const* models, int32_t M, const double* X,
+                       int32_t x_on_device, int64_t N_local, int order, const int32_t* kinds, int32_t nkinds,
+                       const double* noise, const double* pps, double* dc_out, int32_t dc_on_device,
+                       double* best_val, int64_t* best_idx, int64_t idx_offset);
 /* device buffer helpers so a host language without a CUDA binding can stage candidates once */
 int  gpd_dev_alloc(gpd_ctx* ctx, uint64_t bytes, void** out_dev);
 int  gpd_dev_free(gpd_ctx* ctx, void* dev);

@@ -91,8 +91,27 @@ class GPRegression:
             var[s:s + chunk, 0] = Kxx - np.square(tmp).sum(0)
         return mu, var
 
-    def predictive_gradients(self, Xnew, chunk=2048):
-        """GP.predictive_gradients -> mean_jac (N,Q,output_dim), var_jac (N,Q)."""
+    @classmethod
+    def from_posterior(cls, Z, Y, kern, noise_var, L, alpha):
+        """Adopt an already computed posterior (woodbury_chol, woodbury_vector) instead of refactorising: lets the
+        n = 4000 parity cases feed the SAME (alpha, L) to the oracle and to the CUDA path, as GPModel.from_reference
+        does in the other direction.  Hyper-parameters must already be set on ``kern``."""
+        self = cls.__new__(cls)
+        self.X = np.ascontiguousarray(Z, dtype=float)
+        self.Y = np.ascontiguousarray(Y, dtype=float).reshape(len(Z), -1)
+        self.kern = kern
+        self.noise_var = float(noise_var)
+        self._predictive_variable = self.X
+        self.output_dim = self.Y.shape[1]
+        self.posterior = Posterior(np.asarray(L, dtype=float), np.asarray(alpha, dtype=float).reshape(len(Z), -1))
+        return self
+
+    def predictive_gradients(self, Xnew, chunk=2048, want_var=True):
+        """GP.predictive_gradients -> mean_jac (N,Q,output_dim), var_jac (N,Q).
+
+        want_var=False skips the variance Jacobian: GPy always computes it (it needs woodbury_inv = K^-1, an n^3
+        dpotri per GP) and the reference's d_mu_d_p discards it (gp_model.py:217); the large-n parity cases that
+        only need the mean Jacobian switch it off to stay within seconds."""
         Xnew = np.asarray(Xnew, dtype=float)
         N, Q = Xnew.shape
         mean_jac = np.empty((N, Q, self.output_dim))
@@ -103,6 +122,9 @@ class GPRegression:
             for i in range(self.output_dim):
                 mean_jac[s:s + chunk, :, i] = kern.gradients_X(
                     self.posterior.woodbury_vector[:, i:i + 1].T, Xc, Xt)
+            if not want_var:
+                var_jac[s:s + chunk] = np.nan
+                continue
             # d k(x*,x*)/dx* term: stationary => zero (GPy evaluates kern.gradients_X(eye, Xnew))
             dv_dX = np.zeros(Xc.shape)
             alpha = -2.0 * np.dot(kern.K(Xc, Xt), self.posterior.woodbury_inv)

@@ -34,6 +34,7 @@ class OracleGPModel:
         self.Sigma = None
         self.Z = self.Y = self.hyp = self.gps = None
         self.kern_x = None
+        self.want_var_jac = True      # False: d_mu_d_p skips GPy's (discarded) variance Jacobian, see gp.py
 
     dim_b = property(lambda self: len(self.binary_variables))
     non_binary_variables = property(
@@ -140,7 +141,7 @@ class OracleGPModel:
         dmu = np.zeros((len(X), self.dim_p))
         for r, Jr in self._groups(X):
             Z = self.get_Z(X[Jr])
-            dmu[Jr] = self.gps[e][r].predictive_gradients(Z)[0][:, self.dim_x:, 0]
+            dmu[Jr] = self.gps[e][r].predictive_gradients(Z, want_var=self.want_var_jac)[0][:, self.dim_x:, 0]
         return dmu
 
     def _d_s2_d_p(self, e, X):
@@ -190,6 +191,47 @@ class OracleGPModel:
                 ddk = np.sum(kp.gradients_XX(-kx * kiK, Z, gpX), axis=1)[:, dx:, dx:]
                 dds2[I] = -2.0 * (ddk + dkiKdk)
         return dds2
+
+
+def adopt_exact_model(model):
+    """OracleGPModel that shares transforms, hyper-parameters and the posterior (alpha, L) of an exact-GP model object
+    with the reference's attribute surface (a gpdoemd_b200.GPModel, whose GPs expose ``posterior.woodbury_chol`` /
+    ``woodbury_vector`` -- downloaded from the device for device-built GPs): nothing is refactorised, so both sides
+    of a parity check start from the same (alpha, L), like the reference and a GPModel.from_reference copy."""
+    om = OracleGPModel({'name': model.name, 'dim_x': model.dim_x, 'dim_p': model.dim_p, 'num_outputs': model.num_outputs,
+                        'binary_variables': list(model.binary_variables), 'meas_noise_var': model.meas_noise_var})
+    om.Z, om.Y = np.array(model.Z), np.array(model.Y)
+    om.zmin, om.zmax = np.array(model.zmin, dtype=float), np.array(model.zmax, dtype=float)
+    om.xmin, om.xmax = om.zmin[:om.dim_x], om.zmax[:om.dim_x]
+    om.pmin, om.pmax = om.zmin[om.dim_x:], om.zmax[om.dim_x:]
+    om.trans_z, om.trans_x, om.trans_p = BoxTransform(om.zmin, om.zmax), BoxTransform(om.xmin, om.xmax), BoxTransform(om.pmin, om.pmax)
+    om.ymean, om.ystd = np.array(model.ymean, dtype=float), np.array(model.ystd, dtype=float)
+    om.trans_y = MeanTransform(om.ymean, om.ystd)
+    from gpdoemd_b200 import kernels as host_kernels          # class names only (data, no computation)
+    kx = gpy_kernels.KERNELS[host_kernels.kernel_name_of(model.kern_x)]
+    om.kern_x = kx
+    dim = om.dim_x + om.dim_p
+    gps = []
+    for e, row in enumerate(model.gps):
+        gps.append([])
+        for gp in row:
+            if gp is None:
+                gps[e].append(None)
+                continue
+            kernx = kx(om.dim_x - om.dim_b, om.non_binary_variables, 'kernx')
+            kernp = kx(om.dim_p, range(om.dim_x, dim), 'kernp')
+            kern = Prod(kernx, kernp)
+            v = np.asarray(gp[:], dtype=float)
+            k = kern.set_params(v)
+            assert k + 1 == len(v)
+            post = gp.posterior
+            gps[e].append(GPRegression.from_posterior(gp._predictive_variable, gp.Y, kern, v[k], post.woodbury_chol,
+                                                      post.woodbury_vector))
+    om.gps = gps
+    om.hyp = model.hyp
+    om.pmean = None if model.pmean is None else np.array(model.pmean, dtype=float)
+    om.Sigma = None if model.Sigma is None else np.array(model.Sigma, dtype=float)
+    return om
 
 
 class OracleSparseGPModel(OracleGPModel):

@@ -60,3 +60,56 @@ def variance_derivatives_factor_form(om, e, Xt):
     ddk = np.sum(kp.gradients_XX(-kx * beta, Z, gpX), axis=1)[:, dx:, dx:]
     d2s2 = -2.0 * (ddk + np.einsum('ina,inb->nab', W, W))
     return ds2, d2s2
+
+
+def d2mu_truth_longdouble(om, e, Xt, alpha=None):
+    """80-bit truth of the second mean derivative d2 mu_e / dp_a dp_b (transformed units, no binary variables) for the
+    kernels with an exponential profile, from the SAME float64 inputs (training inputs, hyper-parameters, alpha):
+    difference-form distances, every operation in np.longdouble.  SURVEY Appendix A.2 / A.5:
+        d2mu_ab = sum_i alpha_i kx_i sigma_p^2 [ (k''/r^2 - k'/r^3) d_a d_b / (l_a^2 l_b^2) + (k'/r) delta_ab / l_a^2 ]."""
+    ld = np.longdouble
+    gp = om.gps[e][0]
+    kx, kp = gp.kern.kernx, gp.kern.kernp
+    name = type(kx).__name__
+    a = (gp.posterior.woodbury_vector[:, 0] if alpha is None else np.ravel(alpha)).astype(ld)
+    Xtr = gp._predictive_variable.astype(ld)
+    pstar = om.trans_p(om.pmean).astype(ld)
+    Zx = np.asarray(Xt, dtype=float).astype(ld)
+
+    def profile(r):
+        if name == 'Exponential':
+            k = np.exp(-r)
+            return k, -k, k
+        if name == 'Matern32':
+            s3 = np.sqrt(ld(3))
+            ex = np.exp(-s3 * r)
+            return (1 + s3 * r) * ex, -3 * r * ex, 3 * (s3 * r - 1) * ex
+        if name == 'Matern52':
+            s5 = np.sqrt(ld(5))
+            ex = np.exp(-s5 * r)
+            return ((1 + s5 * r + ld(5) / 3 * r * r) * ex, -(ld(5) / 3) * r * (1 + s5 * r) * ex,
+                    (ld(5) / 3) * (5 * r * r - s5 * r - 1) * ex)
+        if name == 'RBF':
+            k = np.exp(-r * r / 2)
+            return k, -r * k, (r * r - 1) * k
+        raise ValueError(name)
+    lx = kx.lengthscale.astype(ld)
+    dxs = (Zx[:, None, kx.active_dims] - Xtr[None, :, kx.active_dims]) / lx
+    rx = np.sqrt((dxs ** 2).sum(-1))
+    kxv = ld(kx.variance) * profile(rx)[0]                                   # (N, n)
+    lp = kp.lengthscale.astype(ld)
+    d = pstar[None, :] - Xtr[:, kp.active_dims]                              # (n, P)
+    r = np.sqrt(((d / lp) ** 2).sum(-1))
+    assert np.all(r > 0), 'p* coincides with a training parameter: GPy special-cases r = 0'
+    k0, k1, k2 = profile(r)
+    P = len(lp)
+    H = np.zeros((len(r), P, P), dtype=ld)
+    c1 = k2 / r ** 2 - k1 / r ** 3
+    c2 = k1 / r
+    for u in range(P):
+        for v in range(P):
+            H[:, u, v] = c1 * d[:, u] * d[:, v] / (lp[u] ** 2 * lp[v] ** 2)
+        H[:, u, u] += c2 / lp[u] ** 2
+    H *= ld(kp.variance)
+    w = kxv * a[None, :]                                                      # (N, n)
+    return np.einsum('ni,iuv->nuv', w, H), float(r.min())

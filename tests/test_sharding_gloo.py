@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from gpdoemd_b200.scoring import ShardedScorer, combine_best, shard_bounds
+from gpdoemd_b200.scoring import ShardedScorer, combine_best, pack_best, shard_bounds, unpack_best
 
 
 def test_shard_bounds_cover_everything():
@@ -31,6 +31,13 @@ def test_combine_best_numpy_argmax_semantics():
     assert i == 10
 
 
+def test_pack_best_round_trips_bit_exactly():
+    vals = [1.5, float('nan'), -0.0, 1e-310, float('inf')]
+    idxs = [0, 7, -1, 2 ** 40, 10 ** 8 - 1]
+    v, i = unpack_best(pack_best(vals, idxs))
+    assert np.array_equal(np.asarray(vals).view(np.int64), v.view(np.int64)) and list(i) == idxs
+
+
 def _worker(rank, world, port, N, seed, out):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
@@ -44,6 +51,15 @@ def _worker(rank, world, port, N, seed, out):
             j = int(np.argmax(dc[lo:hi]))
             return float(dc[lo + j]), lo + j
         v, i = sc.score(N, local)
+        # several criteria in ONE packed all-gather (what a fused multi-criterion pass produces per rank)
+        lo, hi = shard_bounds(N, rank, world)
+        dcs = [dc, -dc, np.where(np.arange(N) == N // 2, np.nan, dc)]
+        if hi > lo:
+            mine = [(float(d[lo + int(np.argmax(d[lo:hi]))]), lo + int(np.argmax(d[lo:hi]))) for d in dcs]
+        else:
+            mine = [(0.0, -1)] * len(dcs)
+        multi = sc.argmax_allgather([m[0] for m in mine], [m[1] for m in mine])
+        assert [m[1] for m in multi] == [int(np.argmax(d)) for d in dcs]
         out[rank] = (v, i, int(np.argmax(dc)), float(dc.max()))
     finally:
         dist.destroy_process_group()
