@@ -197,6 +197,8 @@ class Problem:
         self.models, ds = synthetic.build_models(g.SparseGPModel if sparse else g.GPModel, SEED, cfg['M'], cfg['E'], cfg['D'],
                                                  cfg['P'], cfg['n'], cfg['kernel'], device=local_rank,
                                                  build_on_device=on_dev, **sparse)
+        for mo in self.models:
+            mo.device_handle()            # GP state to the device now (setup, outside every timed region)
         self.lo = np.max([d['xlo'] for d in ds], axis=0)
         self.hi = np.min([d['xhi'] for d in ds], axis=0)
         D = cfg['D']

@@ -181,7 +181,10 @@ def test_build_and_loglik_error_paths(gpu_ctx):
     assert lib.gpd_gauss_loglik(gpu_ctx.handle, dptr(Yo), dptr(Mo), dptr(So), 2, 3, 9, dptr(lp), dptr(mh)) != 0
     assert b'1 <= E <= 8' in lib.gpd_last_error()
     check(lib.gpd_gauss_loglik(gpu_ctx.handle, None, None, None, 0, 3, 2, None, None))
-    # a singular covariance gives the reference's behaviour class: non-finite log-density, not a crash
+    # a singular covariance: scipy's multivariate_normal.logpdf (discrimination_criteria.py:40) raises LinAlgError
+    # ("singular matrix"); the device path reports the zero pivot the same way instead of returning inf / NaN
     from gpdoemd_b200 import discrimination_criteria as gdisc
-    lpz, _ = gdisc._loglik(np.zeros((1, 2)), np.zeros((1, 1, 2)), np.zeros((1, 1, 2, 2)))
-    assert not np.isfinite(lpz[0, 0])
+    with pytest.raises(np.linalg.LinAlgError):
+        gdisc._loglik(np.zeros((1, 2)), np.zeros((1, 1, 2)), np.zeros((1, 1, 2, 2)))
+    lpz, _ = gdisc._loglik(np.zeros((1, 2)), np.zeros((1, 1, 2)), np.tile(np.eye(2), (1, 1, 1, 1)))
+    assert np.isfinite(lpz[0, 0])
