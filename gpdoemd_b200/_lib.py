@@ -76,6 +76,10 @@ _SIGNATURES = {
     'gpd_score_multi': (C.c_int, [C.c_void_p, c_void_pp, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int, c_int32_p,
                                   C.c_int32, c_double_p, c_double_p, C.c_void_p, C.c_int32, c_double_p,
                                   C.POINTER(C.c_int64), C.c_int64]),
+    'gpd_marginals': (C.c_int, [C.c_void_p, c_void_pp, C.c_int32, c_double_p, C.c_int64, C.c_int, c_double_p, c_double_p,
+                                c_void_pp]),
+    'gpd_criterion_resident': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_double_p, c_double_p, c_double_p]),
+    'gpd_resident_free': (None, [C.c_void_p]),
     'gpd_nccl_version': (C.c_int, [c_int32_p]),
     'gpd_nccl_unique_id': (C.c_int, [C.c_char_p]),
     'gpd_comm_init': (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32, c_void_pp]),
@@ -103,11 +107,30 @@ _SIGNATURES = {
 _lib = None
 
 
+def _preload_nccl():
+    """One NCCL per process.  The C library binds NCCL with dlopen("libnccl.so.2") on first use; if that picked the
+    system copy and PyTorch (whose libtorch_cuda.so needs the newer NCCL bundled in the `nvidia-nccl-cu12` wheel) were
+    imported afterwards, the loader would hand torch the older, already loaded soname.  So the wheel's copy, when
+    there is one, is loaded first; a process that already holds a libnccl.so.2 keeps it."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec('nvidia.nccl')
+        for base in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(base, 'lib', 'libnccl.so.2')
+            if os.path.exists(cand):
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return cand
+    except Exception:
+        pass
+    return None
+
+
 def load():
     """Load the shared library and declare every prototype of include/gpdoemd_b200.h."""
     global _lib
     if _lib is not None:
         return _lib
+    _preload_nccl()
     if not os.path.exists(LIB_PATH):
         raise GpdError('%s is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
                        '(or `make -C gpdoemd_b200/csrc`); there is no CPU fallback' % LIB_PATH)

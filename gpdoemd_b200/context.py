@@ -90,6 +90,26 @@ class Context:
         arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
         return arr
 
+    def pooled_pinned(self, shape, dtype=np.float64):
+        """Page-locked array from a per-context pool: the buffer returns to the pool when the array (and every view
+        of it) has been garbage collected, so the drop-in functions can hand out pinned results call after call
+        without paying cudaHostAlloc each time (a D2H copy into pageable memory is staged and ~4x slower)."""
+        import weakref
+        count = int(np.prod(shape))
+        nbytes = max(count * np.dtype(dtype).itemsize, 1)
+        cap = 1 << max(16, (nbytes - 1).bit_length())
+        pool = self.__dict__.setdefault('_pin_pool', {})
+        free = pool.setdefault(cap, [])
+        if free:
+            addr = free.pop()
+        else:
+            p = C.c_void_p()
+            check(self.lib.gpd_host_alloc_pinned(self.handle, cap, C.byref(p)))
+            addr = p.value
+        buf = (C.c_char * cap).from_address(addr)
+        weakref.finalize(buf, free.append, addr)           # numpy keeps `buf` alive as the base of every view
+        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
     def fill_uniform(self, X_dev, N, D, seed, first_row=0, lo=None, hi=None):
         lo = np.zeros(D) if lo is None else _lib.as_f64(lo)
         hi = np.ones(D) if hi is None else _lib.as_f64(hi)

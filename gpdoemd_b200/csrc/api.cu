@@ -1687,6 +1687,165 @@ int gpd_score_multi(gpd_ctx* c, gpd_model* const* models, int32_t M, const doubl
 }
 
 // =================================================================================================
+// marginals of ALL rival models in one pass, kept resident for the criteria (the drop-in call pattern of
+// demos/case_study.py:284-293 without the host round trip of mu / S between taylor_* and HR..JR)
+// =================================================================================================
+}  // extern "C"
+
+struct gpd_resident {
+    gpd_ctx* ctx = nullptr;
+    int64_t N = 0;
+    int M = 0, E = 0;
+    double *mu_dev = nullptr, *S_dev = nullptr;     // (N, M, E) and (N, M, E, E), the layout the criteria take
+};
+
+extern "C" {
+
+void gpd_resident_free(gpd_resident* r) {
+    if (!r) return;
+    cudaSetDevice(r->ctx->device);
+    cudaStreamSynchronize(r->ctx->stream);
+    cudaFree(r->mu_dev);
+    cudaFree(r->S_dev);
+    delete r;
+}
+
+int gpd_marginals(gpd_ctx* c, gpd_model* const* models, int32_t M, const double* X, int64_t N, int order,
+                  double* mu_out, double* S_out, gpd_resident** keep) {
+    GPD_CHECK(c && models && (X || N == 0), "null argument");
+    GPD_CHECK(N >= 0, "negative N");
+    GPD_CHECK(M >= 1 && M <= 64, "number of models out of range (1..64)");
+    GPD_CHECK(order == 1 || order == 2, "order must be 1 or 2");
+    GPD_CHECK(N == 0 || (mu_out && S_out) || keep, "nowhere to put the result");
+    if (keep) *keep = nullptr;
+    GPD_CUDA(cudaSetDevice(c->device));
+    const int E = models[0]->E, D = models[0]->D;
+    int maxP = 0;
+    for (int m = 0; m < M; ++m) {
+        GPD_CHECK(models[m] && models[m]->E == E && models[m]->D == D, "rival models must share num_outputs and dim_x");
+        GPD_CHECK(models[m]->has_sigma, "Sigma is not set on every model (taylor_first_order.py:38 reads model.Sigma)");
+        maxP = std::max(maxP, models[m]->P);
+    }
+    if (N == 0) return 0;
+    NvtxRange nvtx("gpd/marginals");
+    gpd_resident* res = nullptr;
+    if (keep) {
+        res = new gpd_resident();
+        res->ctx = c;
+        res->N = N;
+        res->M = M;
+        res->E = E;
+        cudaError_t e = cudaMalloc(&res->mu_dev, sizeof(double) * (size_t)N * M * E);
+        if (e == cudaSuccess) e = cudaMalloc(&res->S_dev, sizeof(double) * (size_t)N * M * E * E);
+        if (e != cudaSuccess) {
+            set_error(std::string("resident marginals: ") + cudaGetErrorString(e));
+            gpd_resident_free(res);
+            return 1;
+        }
+    }
+    Plan pl;
+    size_t extra = sizeof(double) * (size_t)D;
+    if (!res) extra += sizeof(double) * ((size_t)M * E + (size_t)M * E * E);
+    if (order == 2) extra += sizeof(double) * ((size_t)E * maxP * maxP + E);
+    int rc = plan_build(c, models, M, order_flags(order), N, extra, 0, pl);
+    const size_t total = pl.per_cand_bytes * ((size_t)pl.chunk + kBlk) + (8u << 20) + pl.entries.size() * sizeof(GpView) +
+                         (size_t)pl.entries.size() * pl.tiles * sizeof(Item) * 2;
+    if (!rc) rc = ensure_scratch(c, total);
+    if (rc) {
+        gpd_resident_free(res);
+        return rc;
+    }
+    Bump bump(c->scratch.p, c->scratch.cap);
+    const int Nc = pl.chunk;
+    double* X_dev = bump.take<double>((size_t)Nc * D);
+    double* mu_tmp = res ? nullptr : bump.take<double>((size_t)Nc * M * E);
+    double* S_tmp = res ? nullptr : bump.take<double>((size_t)Nc * M * E * E);
+    double* tmpA = order == 2 ? bump.take<double>((size_t)Nc * E * maxP * maxP) : nullptr;
+    double* tmp_s2 = order == 2 ? bump.take<double>((size_t)Nc * E) : nullptr;
+    rc = plan_materialize(c, pl, bump);
+    cudaStream_t s = c->stream;
+    for (int64_t start = 0; start < N && !rc; start += Nc) {
+        const int nc = (int)std::min<int64_t>(Nc, N - start);
+        double* mu_c = res ? res->mu_dev + (size_t)start * M * E : mu_tmp;
+        double* S_c = res ? res->S_dev + (size_t)start * M * E * E : S_tmp;
+        for (int m = 0; m < M; ++m) {        // finalize writes the means straight into the (N, M, E) layout
+            pl.mb[m].mu = mu_c + (size_t)m * E;
+            pl.mb[m].ldmu = M * E;
+        }
+        rc = run_chunk(c, pl, X_dev, D, nc, X + (size_t)start * D);
+        for (int m = 0; m < M && !rc; ++m) {
+            gpd_model* mo = models[m];
+            const ModelBufs& b = pl.mb[m];
+            const double* Sigma_dev = (const double*)((const char*)mo->xf_dev + offsetof(ModelXform, Sigma));
+            Span sp(c, F_MARG, order == 2 ? 2 : 1, 0);
+            rc = launch_assemble(s, order, nc, E, mo->P, b.mu, b.ldmu, b.s2, b.dmu, b.d2mu, b.d2s2, Sigma_dev,
+                                 S_c + (size_t)m * E * E, M * E * E, tmpA, tmp_s2);
+        }
+        if (!rc && mu_out) {
+            cudaError_t e = cudaMemcpyAsync(mu_out + (size_t)start * M * E, mu_c, sizeof(double) * (size_t)nc * M * E,
+                                            cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(S_out + (size_t)start * M * E * E, S_c, sizeof(double) * (size_t)nc * M * E * E,
+                                    cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) {
+                set_error(std::string("marginals download: ") + cudaGetErrorString(e));
+                rc = 1;
+            }
+        }
+        if (!rc && !res && cudaStreamSynchronize(s) != cudaSuccess) {      // the chunk buffers are reused
+            set_error("marginals: stream synchronisation failed");
+            rc = 1;
+        }
+    }
+    if (!rc && cudaStreamSynchronize(s) != cudaSuccess) {
+        set_error(std::string("marginals: ") + cudaGetErrorString(cudaGetLastError()));
+        rc = 1;
+    }
+    if (rc) {
+        gpd_resident_free(res);
+        return rc;
+    }
+    if (keep) *keep = res;
+    return 0;
+}
+
+int gpd_criterion_resident(gpd_ctx* c, int kind, const gpd_resident* r, const double* noise, const double* pps,
+                           double* dc_out) {
+    GPD_CHECK(c && r && r->ctx == c && noise && pps && dc_out, "null argument or resident marginals of another context");
+    GPD_CHECK(kind >= 0 && kind <= 4, "unknown criterion");
+    const int M = r->M, E = r->E;
+    GPD_CHECK(E >= 1 && E <= kMaxE, "criteria support 1 <= E <= 8 outputs");
+    GPD_CUDA(cudaSetDevice(c->device));
+    const int64_t N = r->N;
+    const size_t per = sizeof(double) + sizeof(double) * criterion_work_doubles(1, M, E);
+    int64_t chunk = std::min<int64_t>(N, std::max<int64_t>(1, (int64_t)((c->scratch_limit - (1 << 20)) / per)));
+    chunk = std::min<int64_t>(chunk, 1 << 24);
+    GPD_TRY(ensure_scratch(c, per * (size_t)chunk + (1 << 20)));
+    Bump bump(c->scratch.p, c->scratch.cap);
+    double* d_dc = bump.take<double>((size_t)chunk);
+    double* d_work = bump.take<double>(criterion_work_doubles((int)chunk, M, E));
+    double* d_noise = bump.take<double>((size_t)E * E);
+    double* d_pps = bump.take<double>(M);
+    GPD_CHECK(bump.off <= bump.cap, "internal: scratch overflow");
+    cudaStream_t s = c->stream;
+    GPD_CUDA(cudaMemcpyAsync(d_noise, noise, sizeof(double) * E * E, cudaMemcpyHostToDevice, s));
+    GPD_CUDA(cudaMemcpyAsync(d_pps, pps, sizeof(double) * M, cudaMemcpyHostToDevice, s));
+    for (int64_t start = 0; start < N; start += chunk) {
+        const int nc = (int)std::min<int64_t>(chunk, N - start);
+        {
+            Span sp(c, F_CRIT, 2, 0);
+            GPD_TRY(launch_criterion(s, kind, r->mu_dev + (size_t)start * M * E, r->S_dev + (size_t)start * M * E * E, nc, M, E,
+                                     d_noise, d_pps, d_dc, d_work));
+        }
+        GPD_CUDA(cudaMemcpyAsync(dc_out + start, d_dc, sizeof(double) * nc, cudaMemcpyDeviceToHost, s));
+        GPD_TRY(singular_fetch(c));
+        GPD_CUDA(cudaStreamSynchronize(s));
+        GPD_TRY(singular_rc(c));
+    }
+    return 0;
+}
+
+// =================================================================================================
 // multi-GPU: candidates sharded, GP state replicated, ONE collective per scoring call
 // =================================================================================================
 }  // extern "C"
@@ -1712,9 +1871,10 @@ static NcclApi* nccl_api() {
     static bool tried = false;
     if (tried) return api.handle ? &api : nullptr;
     tried = true;
-    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
-    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);      // the instance the process already holds, if any
+    if (!h && getenv("GPDOEMD_NCCL_LIB")) h = dlopen(getenv("GPDOEMD_NCCL_LIB"), RTLD_NOW);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW);
     if (!h) return nullptr;
     api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
     api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");

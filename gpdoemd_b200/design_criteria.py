@@ -41,8 +41,14 @@ def _reshape(mu, s2, noise_var=None, pps=None):
 
 
 def _run(kind, mu, s2, noise_var, pps, device=None):
+    from .marginal import resident_pair
+    res = resident_pair(mu, s2)           # untouched outputs of taylor_multi: score the device copy, no upload
     mu, s2v, noise_var, pps, n, M, E = _reshape(mu, s2, noise_var, pps)
     dc = np.empty(n)
+    if res is not None:
+        check(res.ctx.lib.gpd_criterion_resident(res.ctx.handle, _lib.CRITERION_IDS[kind], res.handle,
+                                                 dptr(_lib.as_f64(noise_var)), dptr(_lib.as_f64(pps)), dptr(dc)))
+        return dc, s2v, noise_var
     ctx = get_context(device)
     check(ctx.lib.gpd_criterion(ctx.handle, _lib.CRITERION_IDS[kind], dptr(_lib.as_f64(mu)), dptr(_lib.as_f64(s2v)),
                                 n, M, E, dptr(_lib.as_f64(noise_var)), dptr(_lib.as_f64(pps)), dptr(dc)))
@@ -58,7 +64,7 @@ def BH(mu, s2, noise_var=None, pps=None, mutate_like_reference=False):
     """Box & Hill (1967), Prasad & Someswara Rao (1977) extension   (design_criteria.py:66-92)."""
     dc, s2v, nv = _run('BH', mu, s2, noise_var, pps)
     if mutate_like_reference:
-        s2v += nv
+        s2v += nv            # (read-only taylor_multi outputs raise here: they cannot be mutated and stay resident)
     return dc
 
 

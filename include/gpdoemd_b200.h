@@ -30,7 +30,8 @@ extern "C" {
 typedef struct gpd_ctx gpd_ctx;
 typedef struct gpd_gp gpd_gp;
 typedef struct gpd_model gpd_model;
-typedef struct gpd_comm gpd_comm;   /* one NCCL communicator bound to a context (multi-GPU scoring) */
+typedef struct gpd_comm gpd_comm;
+typedef struct gpd_resident gpd_resident;   /* marginals of all rival models kept in device memory for the criteria */   /* one NCCL communicator bound to a context (multi-GPU scoring) */
 
 /* GPdoemd/kernels/stationary.py:33-99 -- the six ARD stationary kernels */
 enum gpd_kernel {
@@ -210,6 +211,17 @@ int  gpd_score_multi(gpd_ctx* ctx, gpd_model* const* models, int32_t M, const do
                      int64_t N, int order, const int32_t* kinds, int32_t nkinds, const double* noise,
                      const double* pps, double* dc_out, int32_t dc_on_device, double* best_val,
                      int64_t* best_idx, int64_t idx_offset);
+/* ---- the drop-in call pattern without the host round trip (demos/case_study.py:284-293) -------------------------
+ * gpd_marginals = taylor_{first,second}_order for ALL rival models in one pass: mu_out (N,M,E) and S_out (N,M,E,E) are
+ * the arrays the reference's loop `mu[:,i], s2[:,i] = taylor(M_i, X)` fills (either may be NULL).  With keep != NULL the
+ * device copies stay alive in *keep, and gpd_criterion_resident scores them with nothing but dc (N) crossing PCIe.
+ * The host wrapper returns mu / S as read-only arrays so that the resident copy cannot go stale. */
+int  gpd_marginals(gpd_ctx* ctx, gpd_model* const* models, int32_t M, const double* X, int64_t N, int order,
+                   double* mu_out, double* S_out, gpd_resident** keep);
+int  gpd_criterion_resident(gpd_ctx* ctx, int kind, const gpd_resident* marginals, const double* noise /*E,E*/,
+                            const double* pps /*M*/, double* dc_out /*N*/);
+void gpd_resident_free(gpd_resident* marginals);
+
 /* ---- multi-GPU (BASELINE configs[4]): candidates sharded in contiguous blocks, GP state replicated,
  * ONE collective per scoring call = the all-gather of the per-rank (best value, best global index) pairs.  The
  * reference is single-process (demos/case_study.py:279-293 takes np.argmax over the whole grid); these entry points

@@ -5,7 +5,8 @@ criteria: the 11-column first-order bucket; M cut from 8 to 2 so that the oracle
 n=4000, BH), plus P=10 SECOND order (72 / 55-column buckets, gram_kernel<11>) on a smaller training set.  The GPU models
 are built exactly as bench.py builds them (device-side GP build for n >= 2000); the oracle shares their posterior
 (alpha, L) for n >= 2000 -- `oracle.model.adopt_exact_model` -- and refactorises on its own at n = 500.  Candidates:
-421 = 3 full tiles + a ragged one, so tile boundaries and the padded tail are inside the sample."""
+421 = 3 full tiles + a ragged one (C3: 259 = 2 + a ragged one), so tile boundaries and the padded tail are inside
+the sample."""
 import numpy as np
 import pytest
 
@@ -70,7 +71,7 @@ def test_fused_scorer_on_the_baseline_shapes(name, gpu_ctx):
     if cfg['n'] >= 2000:
         gpu_ctx.set_scratch_bytes(16 << 30)
     gms, oms, lo, hi = _problem(cfg, M, adopt=cfg['n'] >= 2000)
-    X = synthetic.candidates(11, 421, cfg['D'], lo, hi)
+    X = synthetic.candidates(11, 259 if name == 'C3' else 421, cfg['D'], lo, hi)   # C3: the second-order oracle is slow
     try:
         _check(cfg, gms, oms, X)
     finally:
