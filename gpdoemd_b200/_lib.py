@@ -76,6 +76,7 @@ _SIGNATURES = {
     'gpd_score_multi': (C.c_int, [C.c_void_p, c_void_pp, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int, c_int32_p,
                                   C.c_int32, c_double_p, c_double_p, C.c_void_p, C.c_int32, c_double_p,
                                   C.POINTER(C.c_int64), C.c_int64]),
+    'gpd_marginal_dx': (C.c_int, [C.c_void_p, c_double_p, C.c_int64] + [c_double_p] * 4),
     'gpd_marginals': (C.c_int, [C.c_void_p, c_void_pp, C.c_int32, c_double_p, C.c_int64, C.c_int, c_double_p, c_double_p,
                                 c_void_pp]),
     'gpd_criterion_resident': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_double_p, c_double_p, c_double_p]),

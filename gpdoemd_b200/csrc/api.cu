@@ -1687,6 +1687,147 @@ int gpd_score_multi(gpd_ctx* c, gpd_model* const* models, int32_t M, const doubl
 }
 
 // =================================================================================================
+// design gradients: first-order Taylor marginal and its derivative with respect to x
+// =================================================================================================
+int gpd_marginal_dx(gpd_model* mo, const double* X, int64_t N, double* mu_out, double* S_out, double* dmu_dx_out,
+                    double* dS_dx_out) {
+    GPD_CHECK(mo && (X || N == 0), "null argument");
+    GPD_CHECK(N >= 0, "negative N");
+    GPD_CHECK(N == 0 || (mu_out && S_out && dmu_dx_out && dS_dx_out), "null output");
+    GPD_CHECK(mo->has_pmean, "pmean is not set (surrogate_model.py:171)");
+    GPD_CHECK(mo->has_sigma, "Sigma is not set (taylor_first_order.py:38 reads model.Sigma)");
+    gpd_ctx* c = mo->ctx;
+    GPD_CUDA(cudaSetDevice(c->device));
+    if (N == 0) return 0;
+    NvtxRange nvtx("gpd/marginal_dx");
+    const int E = mo->E, R = mo->R, D = mo->D, P = mo->P, G = E * R;
+    // every GP of a model shares the kernel class and the active design dimensions (gp_model.py:115-118)
+    const gpd_gp* g0 = nullptr;
+    long long n_pad_sum = 0, n_pad_max = 0;
+    for (gpd_gp* g : mo->gps)
+        if (g) {
+            if (!g0) g0 = g;
+            GPD_CHECK(g->nx == g0->nx, "GPs of one model must share the active design dimensions");
+            n_pad_sum += g->n_pad;
+            n_pad_max = std::max<long long>(n_pad_max, g->n_pad);
+        }
+    GPD_CHECK(g0, "model without any GP");
+    const int nx = g0->nx, NR = 1 + nx, ncol = 1 + P, NG = NR * (NR + 1) / 2;
+    // scratch per candidate: X, 2 panel sets (in / out), contractions, Gram rows, outputs
+    const size_t per = sizeof(double) * ((size_t)D + 2 * (size_t)n_pad_sum * NR + (size_t)G * (NR * ncol + NG) +
+                                         (size_t)E * (1 + E) * (1 + D));
+    GPD_CHECK(c->scratch_limit > (size_t)kBlk * per + (8u << 20), "scratch limit too small for the design-gradient path");
+    int64_t chunk = (int64_t)((c->scratch_limit - (8u << 20)) / per) / kBlk * kBlk;
+    chunk = std::min<int64_t>(chunk, 1 << 20);
+    chunk = std::min<int64_t>(chunk, (N + kBlk - 1) / kBlk * kBlk);
+    GPD_CHECK(chunk >= kBlk, "scratch limit too small");
+    const int Nc = (int)chunk, tiles = Nc / kBlk;
+    GPD_TRY(ensure_scratch(c, per * (size_t)Nc + (8u << 20)));
+    Bump bump(c->scratch.p, c->scratch.cap);
+    double* X_dev = bump.take<double>((size_t)Nc * D);
+    double* pan_in = bump.take<double>((size_t)n_pad_sum * NR * Nc);
+    double* pan_out = bump.take<double>((size_t)n_pad_sum * NR * Nc);
+    double* acc = bump.take<double>((size_t)G * Nc * NR * ncol);
+    double* gram = bump.take<double>((size_t)G * Nc * NG);
+    double* d_mu = bump.take<double>((size_t)Nc * E);
+    double* d_S = bump.take<double>((size_t)Nc * E * E);
+    double* d_dmu = bump.take<double>((size_t)Nc * E * D);
+    double* d_dS = bump.take<double>((size_t)Nc * E * E * D);
+    GpView* views_dev = bump.take<GpView>(G);
+    Item* items_dev = bump.take<Item>((size_t)G * tiles);
+    RawOut* raw_dev = bump.take<RawOut>(1);
+    GPD_CHECK(bump.off <= bump.cap, "internal: scratch overflow");
+    std::vector<GpView> views(G);
+    std::vector<Item> items;
+    long long off_w = 0;
+    for (int gi = 0; gi < G; ++gi) {
+        GpView& v = views[gi];
+        memset(&v, 0, sizeof(v));
+        const gpd_gp* g = mo->gps[gi];
+        if (!g) continue;                       // n == 0 marks "no GP for this binary combination"
+        v.kernel = g->kernel;
+        v.n = g->n;
+        v.n_pad = g->n_pad;
+        v.nblk = g->nblk;
+        v.nx = g->nx;
+        v.P = g->P;
+        v.kss = g->var_x * g->var_p;
+        v.power_x = g->power_x;
+        v.Xs = g->Xs;
+        v.C = g->C;
+        v.G = g->G;
+        v.H = g->H;
+        v.LinvF = g->LinvF;
+        v.LinvB = g->LinvB;
+        for (int d = 0; d < g->nx; ++d) {
+            v.ls[d] = g->ls_x[d];
+            v.x_active[d] = g->x_active[d];
+            v.xmin[d] = mo->xmin[g->x_active[d]];
+            v.xdiff[d] = mo->xmax[g->x_active[d]] - mo->xmin[g->x_active[d]];
+            v.xscale[d] = 1.0 / (v.xdiff[d] * g->ls_x[d]) * (g->kernel == GPD_KERN_RBF ? kRbfCoordScaleHost : 1.0);
+        }
+        v.out_e = gi;                           // one Gram slot per (output, binary combination)
+        v.model = 0;
+        v.panel_off = 0;
+        v.panel_off_w = off_w;
+        off_w += (long long)tiles * g->n_pad * kBlk * NR;
+        for (int t = 0; t < tiles; ++t) items.push_back(Item{gi, t});
+    }
+    RawOut raw;
+    memset(&raw, 0, sizeof(raw));
+    raw.gram = gram;
+    cudaStream_t s = c->stream;
+    GPD_CUDA(cudaMemcpyAsync(views_dev, views.data(), sizeof(GpView) * G, cudaMemcpyHostToDevice, s));
+    GPD_CUDA(cudaMemcpyAsync(items_dev, items.data(), sizeof(Item) * items.size(), cudaMemcpyHostToDevice, s));
+    GPD_CUDA(cudaMemcpyAsync(raw_dev, &raw, sizeof(RawOut), cudaMemcpyHostToDevice, s));
+    XgradArgs a;
+    memset(&a, 0, sizeof(a));
+    a.E = E; a.R = R; a.D = D; a.P = P; a.nx = nx; a.nb = mo->nb; a.ngram = NG;
+    for (int d = 0; d < nx; ++d) a.x_active[d] = g0->x_active[d];
+    for (int v = 0; v < mo->nb; ++v) {
+        a.bcols[v] = mo->binary[v];
+        a.weights[v] = binary_combo_weight(mo->nb, v);
+    }
+    a.xf = mo->xf_dev;
+    a.gps = views_dev;
+    a.X = X_dev;
+    a.ldx = D;
+    a.acc = acc;
+    a.gram = gram;
+    a.mu = d_mu; a.S = d_S; a.dmu = d_dmu; a.dS = d_dS;
+    for (int64_t start = 0; start < N; start += Nc) {
+        const int nc = (int)std::min<int64_t>(Nc, N - start);
+        a.chunk_n = nc;
+        GPD_CUDA(cudaMemcpyAsync(X_dev, X + (size_t)start * D, sizeof(double) * (size_t)nc * D, cudaMemcpyHostToDevice, s));
+        {
+            Span sp(c, F_EVAL, 1, 0);
+            GPD_TRY(launch_xgrad_eval(s, views_dev, G, tiles, X_dev, D, nc, pan_in, acc));
+        }
+        {
+            Span sp(c, F_TRI, 1, 0);
+            GPD_TRY(launch_tri(s, views_dev, items_dev, (int)items.size(), NR, NR, NR, 0, pan_in, pan_out, nullptr, 0, nc,
+                               c->num_sms, c->tri_variant, tri_cps_for(c, Plan()), c->tri_trim));
+        }
+        {
+            Span sp(c, F_GRAM, 1, 0);
+            GPD_TRY(launch_gram(s, views_dev, items_dev, (int)items.size(), NR, pan_out, raw_dev, nc));
+        }
+        {
+            Span sp(c, F_MARG, 1, 0);
+            GPD_TRY(launch_xgrad_finalize(s, a));
+        }
+        GPD_CUDA(cudaMemcpyAsync(mu_out + (size_t)start * E, d_mu, sizeof(double) * (size_t)nc * E, cudaMemcpyDeviceToHost, s));
+        GPD_CUDA(cudaMemcpyAsync(S_out + (size_t)start * E * E, d_S, sizeof(double) * (size_t)nc * E * E, cudaMemcpyDeviceToHost, s));
+        GPD_CUDA(cudaMemcpyAsync(dmu_dx_out + (size_t)start * E * D, d_dmu, sizeof(double) * (size_t)nc * E * D,
+                                 cudaMemcpyDeviceToHost, s));
+        GPD_CUDA(cudaMemcpyAsync(dS_dx_out + (size_t)start * E * E * D, d_dS, sizeof(double) * (size_t)nc * E * E * D,
+                                 cudaMemcpyDeviceToHost, s));
+        GPD_CUDA(cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
+// =================================================================================================
 // marginals of ALL rival models in one pass, kept resident for the criteria (the drop-in call pattern of
 // demos/case_study.py:284-293 without the host round trip of mu / S between taylor_* and HR..JR)
 // =================================================================================================

@@ -72,6 +72,19 @@ struct KmatArgs {                // covariance-matrix build of one GP (kernels_b
     double diag_add;             // Gaussian noise variance + GPy's 1e-8 (+ jitchol jitter)
 };
 
+struct XgradArgs {               // finalize step of the design-gradient path (kernels_xgrad.cu)
+    int E, R, D, P, nx, nb, ngram;
+    int x_active[kMaxXDims];
+    int bcols[kMaxBinary], weights[kMaxBinary];
+    const ModelXform* xf;
+    const GpView* gps;            // E * R views, index e * R + r; missing GPs have n == 0
+    const double* X;
+    int ldx, chunk_n;
+    const double* acc;            // [gp][chunk_n][(1+nx)*(1+P)]
+    const double* gram;           // [gp][chunk_n][ngram]  upper triangle of [v W]^T [v W]
+    double *mu, *S, *dmu, *dS;    // (N,E) (N,E,E) (N,E,D) (N,E,E,D), original units
+};
+
 void set_error(const std::string& msg);
 #define GPD_CUDA(call)                                                                        \
     do {                                                                                      \
@@ -116,6 +129,10 @@ int launch_tri(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int
 int launch_gram(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int nitems, int nrhs,
                 const double* panels, const RawOut* raw_dev, int chunk_n);
 int launch_dmma_probe(cudaStream_t s, int num_sms, int iters, double* sink_dev);
+// kernels_xgrad.cu
+int launch_xgrad_eval(cudaStream_t s, const GpView* gps_dev, int ngp, int tiles, const double* X_dev, int ldx, int chunk_n,
+                      double* panels, double* acc);
+int launch_xgrad_finalize(cudaStream_t s, const XgradArgs& a);
 // kernels_build.cu
 int launch_kmat(cudaStream_t s, const KmatArgs& a, const double* Z_dev, double* A_dev);
 int launch_cholesky(cudaStream_t s, double* A_dev, int n, int* info_dev, uint64_t* launches);

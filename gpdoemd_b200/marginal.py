@@ -130,6 +130,23 @@ def _assemble(model, xnew, order, device=None):
     return M, S
 
 
+def taylor_first_order_dx(model, xnew):
+    """``taylor_first_order`` and its derivative with respect to the design:
+    ``(model, xnew) -> M (N,E), S (N,E,E), dM_dx (N,E,D), dS_dx (N,E,E,D)`` in original units (the
+    reference has no counterpart).  Columns of binary design variables hold zero."""
+    assert isinstance(model, GPModel), 'design gradients need a gpdoemd_b200 GP model'
+    assert model.pmean is not None and model.Sigma is not None, 'pmean / Sigma are not set'
+    X = _lib.as_f64(xnew)
+    assert X.ndim == 2 and X.shape[1] == model.dim_x
+    N, E, D = len(X), model.num_outputs, model.dim_x
+    model.check_routing(X)
+    M, S = np.empty((N, E)), np.empty((N, E, E))
+    dM, dS = np.empty((N, E, D)), np.empty((N, E, E, D))
+    ctx = get_context(model._device)
+    check(ctx.lib.gpd_marginal_dx(model.device_handle(), dptr(X), N, dptr(M), dptr(S), dptr(dM), dptr(dS)))
+    return M, S, dM, dS
+
+
 def taylor_first_order(model, xnew):
     if isinstance(model, GPModel):
         return _device_marginal(model, xnew, 1)

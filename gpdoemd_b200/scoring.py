@@ -121,9 +121,58 @@ def score_designs_dev(models, X_dev, N, order=1, criterion='BH', noise_var=None,
     return int(bi.value), bv.value
 
 
+def criterion_with_gradient(models, X, criterion='BH', noise_var=None, pps=None):
+    """Criterion value and its gradient with respect to the design at the rows of X (first-order Taylor marginals):
+    ``-> f (K,), g (K, D)``.  Device: ``gpd_marginal_dx`` per rival model; host: the chain rule through the criterion
+    (design_gradients.py).  HR, BH, BF, AW."""
+    from .design_gradients import criterion_gradient
+    from .marginal import taylor_first_order_dx
+    X = np.array(X, dtype=float, ndmin=2)
+    K, D = X.shape
+    M, E = len(models), models[0].num_outputs
+    mu, S = np.empty((K, M, E)), np.empty((K, M, E, E))
+    dmu, dS = np.empty((K, M, E, D)), np.empty((K, M, E, E, D))
+    for i, m in enumerate(models):
+        mu[:, i], S[:, i], dmu[:, i], dS[:, i] = taylor_first_order_dx(m, X)
+    return criterion_gradient(criterion, mu, S, dmu, dS, noise_var, pps)
+
+
+def _refine_lbfgs(models, X, lo, hi, free, criterion, noise_var, pps, iters, value_and_grad=None):
+    """Joint bound-constrained L-BFGS over all start points: the objective sum_k f(x_k) is separable, so one
+    iteration = ONE batched device pass over the K current points (values and gradients)."""
+    from scipy.optimize import minimize
+    K, D = X.shape
+    if value_and_grad is None:
+        def value_and_grad(Xb):
+            return criterion_with_gradient(models, Xb, criterion, noise_var, pps)
+    scale = np.maximum(hi - lo, 1e-300)[free]                    # optimise in box units
+    evals = [0]
+
+    def fg(z):
+        Xb = X.copy()
+        Xb[:, free] = lo[free] + z.reshape(K, len(free)) * scale
+        f, g = value_and_grad(Xb)
+        evals[0] += K
+        f = np.where(np.isfinite(f), f, -1e300)
+        g = np.where(np.isfinite(g), g, 0.0)
+        return -float(np.sum(f)), -(g[:, free] * scale).ravel()
+    z0 = ((X[:, free] - lo[free]) / scale).ravel()
+    res = minimize(fg, z0, jac=True, method='L-BFGS-B', bounds=[(0.0, 1.0)] * len(z0),
+                   options={'maxiter': int(iters), 'maxfun': int(4 * iters) + 4, 'ftol': 1e-15, 'gtol': 1e-10})
+    Xr = X.copy()
+    Xr[:, free] = lo[free] + np.clip(res.x.reshape(K, len(free)), 0.0, 1.0) * scale
+    return Xr, evals[0]
+
+
 def refine_designs(models, X_start, criterion='BH', order=1, noise_var=None, pps=None, bounds=None, binary=(),
-                   step=None, iters=25, shrink=0.5, tol=1e-6, scorer=None):
-    """Continuous refinement of the best grid designs: batched compass (pattern) search.
+                   step=None, iters=25, shrink=0.5, tol=1e-6, scorer=None, method='auto', value_and_grad=None):
+    """Continuous refinement of the best grid designs.
+
+    method='lbfgs' (default for first order + HR/BH/BF/AW): bound-constrained L-BFGS on the analytic design gradient
+    (``criterion_with_gradient``: x-derivatives of mu and S on the device, chain rule through the criterion on the
+    host), all start points in one batch per iteration; the result of every point is then re-scored by the fused
+    scorer and kept only if it improves on its start, and a short compass search polishes it.  method='compass'
+    (JR, second order): the batched derivative-free pattern search described below.
 
     The reference only evaluates a fixed candidate set and takes ``np.argmax`` (demos/case_study.py:279-293).  Here
     every start point (e.g. the top-k designs of the grid) is improved by polling the 2 * D axis neighbours at the
@@ -147,14 +196,28 @@ def refine_designs(models, X_start, criterion='BH', order=1, noise_var=None, pps
     assert lo.shape == (D,) and hi.shape == (D,) and np.all(hi >= lo)
     free = np.array([d for d in range(D) if d not in set(binary)], dtype=int)
     assert len(free) > 0, 'no continuous design dimension to refine'
-    h0 = 0.05 * (hi - lo) if step is None else np.broadcast_to(np.asarray(step, dtype=float), (D,))
-    H = np.tile(h0, (K, 1))                       # per-point step lengths
     if scorer is None:
         def scorer(Xb):
             return score_designs(models, Xb, order=order, criterion=criterion, noise_var=noise_var, pps=pps)[2]
     X = np.clip(X, lo, hi)
     f = np.array(scorer(X), dtype=float)
     evals = K
+    from .design_gradients import SUPPORTED
+    if method == 'auto':
+        method = 'lbfgs' if (order == 1 and criterion in SUPPORTED and (models is not None or value_and_grad is not None)) else 'compass'
+    assert method in ('lbfgs', 'compass')
+    if method == 'lbfgs':
+        assert order == 1 and criterion in SUPPORTED, 'analytic design gradients: first order, %s' % (SUPPORTED,)
+        Xr, ne = _refine_lbfgs(models, X, lo, hi, free, criterion, noise_var, pps, iters, value_and_grad)
+        fr = np.array(scorer(Xr), dtype=float)
+        evals += ne + K
+        better = fr > f                                        # NaN never wins; monotone per start point
+        X[better], f[better] = Xr[better], fr[better]
+        iters = min(iters, 6)                                  # short derivative-free polish (bound corners, kinks of the clip)
+        H0 = 0.002 * (hi - lo)
+        step = H0 if step is None else np.minimum(np.broadcast_to(np.asarray(step, dtype=float), (D,)), H0)
+    h0 = 0.05 * (hi - lo) if step is None else np.broadcast_to(np.asarray(step, dtype=float), (D,))
+    H = np.tile(h0, (K, 1))                       # per-point step lengths
     dirs = np.concatenate([np.eye(D)[free], -np.eye(D)[free]])          # (2F, D)
     for _ in range(iters):
         active = np.any(H[:, free] > tol * np.maximum(hi - lo, 1e-300)[free], axis=1)

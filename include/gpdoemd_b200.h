@@ -211,6 +211,13 @@ int  gpd_score_multi(gpd_ctx* ctx, gpd_model* const* models, int32_t M, const do
                      int64_t N, int order, const int32_t* kinds, int32_t nkinds, const double* noise,
                      const double* pps, double* dc_out, int32_t dc_on_device, double* best_val,
                      int64_t* best_idx, int64_t idx_offset);
+/* ---- design gradients (refining the grid argmax of demos/case_study.py:279-293) --------------------
+ * taylor_first_order (marginal/taylor_first_order.py:27-43) together with its derivative with respect to the design:
+ * mu (N,E), S (N,E,E), dmu_dx (N,E,D), dS_dx (N,E,E,D), ORIGINAL units; columns of binary design variables hold 0.
+ * The reference has no such gradient (it only evaluates a grid); parity = central finite differences of the marginal. */
+int  gpd_marginal_dx(gpd_model* model, const double* X, int64_t N, double* mu_out, double* S_out,
+                     double* dmu_dx_out, double* dS_dx_out);
+
 /* ---- the drop-in call pattern without the host round trip (demos/case_study.py:284-293) -------------------------
  * gpd_marginals = taylor_{first,second}_order for ALL rival models in one pass: mu_out (N,M,E) and S_out (N,M,E,E) are
  * the arrays the reference's loop `mu[:,i], s2[:,i] = taylor(M_i, X)` fills (either may be NULL).  With keep != NULL the
