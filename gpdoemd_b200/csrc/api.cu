@@ -55,6 +55,7 @@ struct gpd_ctx {
     cudaStream_t stream2 = nullptr;         // low priority: only the evaluation overlapped with a tail wave (run_chunk)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int tail_overlap = 1;                   // option "tail_overlap"
+    int fused = 0;                          // option "fused": first-order path through the fused evaluation + contraction kernel
     uint64_t scratch_limit = 6ull << 30;
     DevBuf scratch, tables, flush;
     uint64_t launches = 0;
@@ -188,6 +189,7 @@ struct Group {          // GPs evaluated by one eval launch: same kernel class, 
     std::vector<int> entries;
     int item_begin = 0, item_count = 0;
     int head_begin = 0, head_count = 0, big_begin = 0, big_count = 0;   // in Plan::items2_dev (tail overlap)
+    int fitem_begin = 0, fitem_count = 0;                               // in Plan::fitems_dev (fused path)
 };
 struct ModelBufs {
     RawOut raw;
@@ -218,6 +220,13 @@ struct Plan {
     double *panels_in = nullptr, *panels_out = nullptr, *panels_beta = nullptr;
     int nitems = 0;
     Bump* bump = nullptr;
+    // fused evaluation + contraction (first order): no per-candidate panels, one private panel per CTA instead
+    bool fused = false;
+    FItem* fitems_dev = nullptr;
+    double* priv = nullptr;
+    long long priv_stride = 0;
+    int fused_parts = 1;            // max parts an item is cut into (tail wave); ||v||^2 slots = 2 * fused_parts
+    size_t fixed_bytes = 0;         // scratch that does not scale with the chunk (private panels, fused item list)
 };
 
 }  // namespace gpd
@@ -282,7 +291,7 @@ static int plan_build(gpd_ctx* c, gpd_model* const* models, int M, int flags, lo
             }
         // raws + hook outputs, bytes per candidate
         const int ncols = ncols_for(flags, P);
-        const int ng = pl.need_W ? nrhs * (nrhs + 1) / 2 : 4;
+        const int ng = pl.need_W ? nrhs * (nrhs + 1) / 2 : 8;      // first order: up to 2 row groups x 4 parts
         size_t d = (size_t)E * (ncols + 1 + ng + ((flags & WANT_D2S2) ? npair : 0));
         d += (size_t)E * 2;
         if (flags & WANT_DMU) d += (size_t)E * P;
@@ -293,9 +302,22 @@ static int plan_build(gpd_ctx* c, gpd_model* const* models, int M, int flags, lo
         if (mo->nb) per_cand += sizeof(int) * mo->R;
     }
     GPD_CHECK(!pl.entries.empty(), "no GP surrogates in the models");
+    // first order (one right-hand side, mean + first derivative columns only): the fused kernel keeps the panel of the
+    // item in flight in a private L2-resident region per CTA, nothing panel-sized is allocated per candidate
+    long long n_pad_max = 0;
+    pl.fused = c->fused && !pl.need_W && !(flags & WANT_D2MU);
+    for (auto& grp : pl.groups)
+        if (ncols_for(flags, grp.P) > 11 || grp.nx > kMaxXDims) pl.fused = false;
+    for (auto& en : pl.entries) n_pad_max = std::max<long long>(n_pad_max, en.gp->n_pad);
+    pl.priv_stride = n_pad_max * kFusedTile;      // per CTA: n_pad x tile candidates
     // panels: in (max_nrhs kinds), out (only when W is needed), beta (only for d2s2)
     int kinds = pl.max_nrhs + (pl.need_W ? pl.max_nrhs : 0) + ((flags & WANT_D2S2) ? 1 : 0);
-    per_cand += (size_t)pl.panel_unit * kinds * sizeof(double);
+    pl.fixed_bytes = 0;
+    if (pl.fused) {
+        pl.fixed_bytes = sizeof(double) * (size_t)pl.priv_stride * kFusedCtasPerSm * c->num_sms + sizeof(FItem) * 16 * (size_t)c->num_sms + (1 << 16);
+        extra_fixed += pl.fixed_bytes;
+        per_cand += (2 * sizeof(FItem) * pl.entries.size() + kBlk - 1) / kBlk; // one FItem per (GP, half tile)
+    } else per_cand += (size_t)pl.panel_unit * kinds * sizeof(double);
     pl.per_cand_bytes = per_cand;
     const size_t fixed = extra_fixed + (size_t)(1 << 20) +
                          pl.entries.size() * (sizeof(GpView) + 64) +
@@ -340,9 +362,60 @@ static int plan_build(gpd_ctx* c, gpd_model* const* models, int M, int flags, lo
 }
 
 // carve the scratch region and upload the static descriptor tables for this plan
+// cut the row blocks [0, nblk) of a tail item into s contiguous parts of (nearly) equal cost; the cost of part [a, b) is
+// its triangular tile count sum_{I=a}^{b-1} (I + 1) plus kE * b for re-evaluating the k rows it needs -> s + 1 bounds
+static std::vector<int> split_rows(int nblk, int s, double kE) {
+    s = std::max(1, std::min(s, nblk));
+    auto cost = [&](int a, int b) { return 0.5 * ((double)b * (b + 1) - (double)a * (a + 1)) + kE * b; };
+    std::vector<std::vector<double>> best(s + 1, std::vector<double>(nblk + 1, 1e300));
+    std::vector<std::vector<int>> from(s + 1, std::vector<int>(nblk + 1, 0));
+    best[0][0] = 0.0;
+    for (int k = 1; k <= s; ++k)
+        for (int b = k; b <= nblk; ++b)
+            for (int a = k - 1; a < b; ++a) {
+                const double v = std::max(best[k - 1][a], cost(a, b));
+                if (v < best[k][b]) { best[k][b] = v; from[k][b] = a; }
+            }
+    std::vector<int> bounds(s + 1);
+    bounds[s] = nblk;
+    for (int k = s; k >= 1; --k) bounds[k - 1] = from[k][bounds[k]];
+    return bounds;
+}
+
+// items of the fused kernel for one group: whole (GP, tile) items for the complete waves of the persistent grid, the
+// remainder (the partial last wave, or everything when there is less than one wave) cut into row-block parts
+static void fused_items_for(const gpd_ctx* c, const Plan& pl, const Group& grp, std::vector<FItem>& out, int* max_parts) {
+    const int S = kFusedCtasPerSm * c->num_sms;
+    std::vector<std::pair<int, int>> all;     // (entry, tile of kFusedTile candidates), tile-major: one wave touches every factor
+    for (int t = 0; t < kFusedCtasPerSm * pl.tiles; ++t)
+        for (int ei : grp.entries) all.push_back({ei, t});
+    const int nit = (int)all.size(), n_full = nit / S * S, rem = nit - n_full;
+    int s = rem > 0 ? std::min(4, S / rem) : 1;
+    if (!c->tail_overlap) s = 1;              // the same switch disables the tail treatment of both paths
+    for (int k = 0; k < nit; ++k) {
+        const gpd_gp* g = pl.entries[all[k].first].gp;
+        if (k < n_full || s < 2 || g->nblk < 2) {
+            out.push_back(FItem{all[k].first, all[k].second, 0, (short)g->nblk, 0, 1});
+            continue;
+        }
+        const std::vector<int> b = split_rows(g->nblk, s, 0.2);
+        const int np = (int)b.size() - 1;
+        *max_parts = std::max(*max_parts, np);
+        for (int p = 0; p < np; ++p) out.push_back(FItem{all[k].first, all[k].second, (short)b[p], (short)b[p + 1], (short)p, (short)np});
+    }
+}
+
 static int plan_materialize(gpd_ctx* c, Plan& pl, Bump& bump) {
     const int M = (int)pl.models.size();
     const int Nc = pl.chunk;
+    std::vector<FItem> fitems;
+    pl.fused_parts = 1;
+    if (pl.fused)
+        for (auto& grp : pl.groups) {
+            grp.fitem_begin = (int)fitems.size();
+            fused_items_for(c, pl, grp, fitems, &pl.fused_parts);
+            grp.fitem_count = (int)fitems.size() - grp.fitem_begin;
+        }
     pl.mb.assign(M, ModelBufs());
     std::vector<RawOut> raws(M);
     for (int m = 0; m < M; ++m) {
@@ -351,7 +424,7 @@ static int plan_materialize(gpd_ctx* c, Plan& pl, Bump& bump) {
         const int nrhs = pl.need_W ? 1 + P : 1;
         ModelBufs& b = pl.mb[m];
         b.ldraw = ncols_for(pl.flags, P);
-        b.ng = pl.need_W ? nrhs * (nrhs + 1) / 2 : tri_row_groups(c->tri_variant);
+        b.ng = pl.need_W ? nrhs * (nrhs + 1) / 2 : (pl.fused ? 2 * pl.fused_parts : tri_row_groups(c->tri_variant));
         b.raw.cmu = bump.take<double>((size_t)E * Nc * b.ldraw);
         b.raw.kss = bump.take<double>((size_t)E * Nc);
         b.raw.gram = bump.take<double>((size_t)E * Nc * b.ng);
@@ -369,7 +442,9 @@ static int plan_materialize(gpd_ctx* c, Plan& pl, Bump& bump) {
         }
         raws[m] = b.raw;
     }
-    const size_t panel_doubles = (size_t)pl.panel_unit * Nc;
+    const size_t panel_doubles = pl.fused ? 0 : (size_t)pl.panel_unit * Nc;
+    pl.priv = pl.fused ? bump.take<double>((size_t)pl.priv_stride * kFusedCtasPerSm * c->num_sms) : nullptr;
+    pl.fitems_dev = pl.fused ? bump.take<FItem>(fitems.size()) : nullptr;
     pl.panels_in = bump.take<double>(panel_doubles * pl.max_nrhs);
     pl.panels_out = pl.need_W ? bump.take<double>(panel_doubles * pl.max_nrhs) : nullptr;
     pl.panels_beta = (pl.flags & WANT_D2S2) ? bump.take<double>(panel_doubles) : nullptr;
@@ -431,7 +506,7 @@ static int plan_materialize(gpd_ctx* c, Plan& pl, Bump& bump) {
     std::vector<Item> items2;
     pl.head_tiles = 0;
     pl.n_head = pl.n_big = 0;
-    if (c->tail_overlap && !pl.need_W) {
+    if (c->tail_overlap && !pl.need_W && !pl.fused) {
         const long long S = c->num_sms, G = (long long)pl.entries.size();
         long long a = S, b = G;
         while (b) { const long long t = a % b; a = b; b = t; }      // a = gcd(S, G)
@@ -461,6 +536,8 @@ static int plan_materialize(gpd_ctx* c, Plan& pl, Bump& bump) {
     if (pl.items2_dev)
         GPD_CUDA(cudaMemcpyAsync(pl.items2_dev, items2.data(), sizeof(Item) * items2.size(), cudaMemcpyHostToDevice, c->stream));
     GPD_CUDA(cudaMemcpyAsync(pl.raws_dev, raws.data(), sizeof(RawOut) * M, cudaMemcpyHostToDevice, c->stream));
+    if (pl.fused)
+        GPD_CUDA(cudaMemcpyAsync(pl.fitems_dev, fitems.data(), sizeof(FItem) * fitems.size(), cudaMemcpyHostToDevice, c->stream));
     // pageable-source cudaMemcpyAsync returns once the data is staged: the host vectors may go out of scope
     return 0;
 }
@@ -484,7 +561,7 @@ static int run_chunk(gpd_ctx* c, Plan& pl, double* X_dev, int ldx, int nc, const
     NvtxRange nvtx_chunk("gpd/run_chunk");
     bool any_binary = false;
     for (int m = 0; m < M; ++m) any_binary = any_binary || pl.models[m]->nb > 0;
-    const bool overlap = pl.head_tiles > 0 && !pl.need_W && nc > pl.head_tiles * kBlk;
+    const bool overlap = !pl.fused && pl.head_tiles > 0 && !pl.need_W && nc > pl.head_tiles * kBlk;
     // rows the main stream needs before its first kernel: all of them when a routing pass reads X, else the head tiles
     const size_t head_rows = (X_host && overlap && !any_binary) ? (size_t)pl.head_tiles * kBlk : (size_t)nc;
     if (X_host)
@@ -507,6 +584,40 @@ static int run_chunk(gpd_ctx* c, Plan& pl, double* X_dev, int ldx, int nc, const
     // count check (identity routing uses chunk_n = nc).
     (void)tiles_used;
     double n2sum = 0;   // algorithmic flops: n^2 per candidate per right-hand side
+    if (pl.fused) {
+        // K1 + K2 in one persistent launch per group; the panel of an item lives in the CTA's private L2-resident region
+        if (pl.fused_parts > 1)     // slots of the items that are not cut into parts must read as zero
+            for (int m = 0; m < M; ++m)
+                if (!pl.models[m]->nb)
+                    GPD_CUDA(cudaMemsetAsync(pl.mb[m].raw.gram, 0, sizeof(double) * (size_t)pl.models[m]->E * Nc * pl.mb[m].ng, s));
+        for (auto& grp : pl.groups) {
+            const int ncols = ncols_for(pl.flags, grp.P);
+            double fl = 0;
+            for (int ei : grp.entries) {
+                const gpd_gp* g = pl.entries[ei].gp;
+                fl += (double)nc * (double)g->n * g->n / pl.models[pl.entries[ei].model]->R;
+            }
+            FusedArgs fa;
+            fa.gps = pl.views_dev;
+            fa.items = pl.fitems_dev + grp.fitem_begin;
+            fa.nitems = grp.fitem_count;
+            fa.X = X_dev;
+            fa.ldx = ldx;
+            fa.chunk_n = nc;
+            fa.priv = pl.priv;
+            fa.priv_stride = pl.priv_stride;
+            fa.raws = pl.raws_dev;
+            fa.ldraw = pl.mb[pl.entries[grp.entries[0]].model].ldraw;
+            fa.ncols = ncols;
+            fa.ng = 2 * pl.fused_parts;
+            fa.trim = c->tri_trim;
+            const int grid = std::min(grp.fitem_count, kFusedCtasPerSm * c->num_sms);
+            Span sp(c, F_TRI, 1, fl);
+            const int rc = launch_fused(s, grp.kernel, grid, grp.nx, ncols, fa);
+            GPD_CHECK(rc >= 0, "internal: no fused kernel variant for a shape the planner accepted");
+            if (rc) return rc;
+        }
+    } else
     if (overlap) {
         GPD_CUDA(cudaEventRecord(c->ev_fork, s));
         GPD_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
@@ -514,7 +625,7 @@ static int run_chunk(gpd_ctx* c, Plan& pl, double* X_dev, int ldx, int nc, const
             GPD_CUDA(cudaMemcpyAsync(X_dev + head_rows * ldx, X_host + head_rows * ldx,
                                      sizeof(double) * ((size_t)nc - head_rows) * ldx, cudaMemcpyHostToDevice, c->stream2));
     }
-    for (int pass = 0; pass < (overlap ? 2 : 1); ++pass) {
+    for (int pass = 0; pass < (pl.fused ? 0 : (overlap ? 2 : 1)); ++pass) {
         // pass 0: all items (or the head tiles) on the main, high-priority stream; pass 1: the remaining tiles on the
         // second stream, concurrently with the head's evaluation and triangular launch
         cudaStream_t es = pass ? c->stream2 : s;
@@ -549,7 +660,9 @@ static int run_chunk(gpd_ctx* c, Plan& pl, double* X_dev, int ldx, int nc, const
         GPD_TRY(launch_tri(s, pl.views_dev, pl.items2_dev + pl.n_head, pl.n_big, 1, 1, 1, 0, pl.panels_in, nullptr, pl.raws_dev,
                            tri_row_groups(c->tri_variant), nc, c->num_sms, c->tri_variant, tri_cps_for(c, pl), c->tri_trim));
     } else
-    if (!pl.need_W) {
+    if (pl.fused) {
+        // evaluation and contraction already ran in the fused launch above
+    } else if (!pl.need_W) {
         Span sp(c, F_TRI, 1, n2sum);
         GPD_TRY(launch_tri(s, pl.views_dev, pl.items_dev, pl.nitems, 1, 1, 1, 0, pl.panels_in, nullptr, pl.raws_dev,
                            tri_row_groups(c->tri_variant), nc, c->num_sms, c->tri_variant, tri_cps_for(c, pl),
@@ -712,6 +825,11 @@ int gpd_set_option(gpd_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "tail_overlap")) {
         GPD_CHECK(value == 0 || value == 1, "tail_overlap is 0 or 1");
         c->tail_overlap = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "fused")) {
+        GPD_CHECK(value == 0 || value == 1, "fused is 0 or 1");
+        c->fused = (int)value;
         return 0;
     }
     if (!strcmp(name, "tri_trim")) {
@@ -1261,7 +1379,7 @@ static int hooks_host(gpd_model* mo, const double* X, int64_t N, int flags, cons
     pl.transformed = transformed;
     const int D = mo->D, E = mo->E, P = mo->P;
     GPD_TRY(plan_build(c, &mo, 1, flags, N, sizeof(double) * D, 0, pl));
-    const size_t total = pl.per_cand_bytes * ((size_t)pl.chunk + kBlk) + (8u << 20) + pl.entries.size() * sizeof(GpView) +
+    const size_t total = pl.per_cand_bytes * ((size_t)pl.chunk + kBlk) + (8u << 20) + pl.fixed_bytes + pl.entries.size() * sizeof(GpView) +
                          (size_t)pl.entries.size() * pl.tiles * sizeof(Item) * 2;
     GPD_TRY(ensure_scratch(c, total));
     Bump bump(c->scratch.p, c->scratch.cap);
@@ -1350,7 +1468,7 @@ int gpd_marginal(gpd_model* mo, const double* X, int64_t N, int order, double* m
     Plan pl;
     const size_t extra = sizeof(double) * ((size_t)D + (size_t)E * E + (order == 2 ? (size_t)E * P * P + E : 0));
     GPD_TRY(plan_build(c, &mo, 1, order_flags(order), N, extra, 0, pl));
-    const size_t total = pl.per_cand_bytes * ((size_t)pl.chunk + kBlk) + (8u << 20) + pl.entries.size() * sizeof(GpView) +
+    const size_t total = pl.per_cand_bytes * ((size_t)pl.chunk + kBlk) + (8u << 20) + pl.fixed_bytes + pl.entries.size() * sizeof(GpView) +
                          (size_t)pl.entries.size() * pl.tiles * sizeof(Item) * 2;
     GPD_TRY(ensure_scratch(c, total));
     Bump bump(c->scratch.p, c->scratch.cap);
@@ -1571,7 +1689,7 @@ static int score_impl(gpd_ctx* c, gpd_model* const* models, int32_t M, const dou
         if (!x_on_device) extra += sizeof(double) * D;
         if (order == 2) extra += sizeof(double) * ((size_t)E * maxP * maxP + E);
         GPD_TRY(plan_build(c, models, M, order_flags(order), N, extra, 0, pl));
-        const size_t total = pl.per_cand_bytes * ((size_t)pl.chunk + kBlk) + (8u << 20) + pl.entries.size() * sizeof(GpView) +
+        const size_t total = pl.per_cand_bytes * ((size_t)pl.chunk + kBlk) + (8u << 20) + pl.fixed_bytes + pl.entries.size() * sizeof(GpView) +
                              (size_t)pl.entries.size() * pl.tiles * sizeof(Item) * 2;
         GPD_TRY(ensure_scratch(c, total));
         Bump bump(c->scratch.p, c->scratch.cap);
@@ -1889,7 +2007,7 @@ int gpd_marginals(gpd_ctx* c, gpd_model* const* models, int32_t M, const double*
     if (!res) extra += sizeof(double) * ((size_t)M * E + (size_t)M * E * E);
     if (order == 2) extra += sizeof(double) * ((size_t)E * maxP * maxP + E);
     int rc = plan_build(c, models, M, order_flags(order), N, extra, 0, pl);
-    const size_t total = pl.per_cand_bytes * ((size_t)pl.chunk + kBlk) + (8u << 20) + pl.entries.size() * sizeof(GpView) +
+    const size_t total = pl.per_cand_bytes * ((size_t)pl.chunk + kBlk) + (8u << 20) + pl.fixed_bytes + pl.entries.size() * sizeof(GpView) +
                          (size_t)pl.entries.size() * pl.tiles * sizeof(Item) * 2;
     if (!rc) rc = ensure_scratch(c, total);
     if (rc) {

@@ -44,6 +44,19 @@ struct GpView {
 // Work item of the evaluation / triangular kernels: GP + candidate tile (128 columns).
 struct Item { int gp; int tile; };
 
+// Fused evaluation + contraction kernel (fused_impl.cuh): candidates per work item and CTAs per SM.  128 / 1 = one
+// 512-thread CTA per SM (3 x 32 k pipeline stages); 64 / 2 = two 256-thread CTAs per SM on half tiles (4 x 16 k), which
+// was measured slower at every size (profiles/r02_summary.md) and is kept as a compile-time variant only.
+#ifndef GPD_FUSED_TILE
+#define GPD_FUSED_TILE 128
+#endif
+constexpr int kFusedTile = GPD_FUSED_TILE;
+constexpr int kFusedCtasPerSm = kBlk / kFusedTile;
+
+// Work item of the fused evaluation + contraction kernel: row blocks [I0, I1) of (GP, tile); the parts of one (GP, tile)
+// write their ||v||^2 partials to distinct slots
+struct FItem { int gp; int tile; short I0, I1; short part, nparts; };
+
 // Per-model raw outputs for a chunk (device pointers), transformed units.
 struct RawOut {
     double* cmu;    // [E][Nc][ldraw]  kx . C columns
@@ -70,6 +83,19 @@ struct KmatArgs {                // covariance-matrix build of one GP (kernels_b
     double ls_x[kMaxXDims], ls_p[kMaxP];
     double var_x, var_p, power_x, power_p;
     double diag_add;             // Gaussian noise variance + GPy's 1e-8 (+ jitchol jitter)
+};
+
+struct FusedArgs {                // fused_impl.cuh
+    const GpView* gps;
+    const FItem* items;
+    int nitems;
+    const double* X;
+    int ldx, chunk_n;
+    double* priv;              // [gridDim.x][priv_stride] private right-hand-side panels
+    long long priv_stride;     // doubles per CTA (>= n_pad_max * 128)
+    const RawOut* raws;
+    int ldraw, ncols, ng;      // ng = row length of raw.gram (= 2 * max parts)
+    int trim;
 };
 
 struct XgradArgs {               // finalize step of the design-gradient path (kernels_xgrad.cu)
@@ -129,6 +155,8 @@ int launch_tri(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int
 int launch_gram(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int nitems, int nrhs,
                 const double* panels, const RawOut* raw_dev, int chunk_n);
 int launch_dmma_probe(cudaStream_t s, int num_sms, int iters, double* sink_dev);
+// kernels_fused.cu: K1 + K2 in one persistent kernel (first-order path); returns -1 when no variant covers the shape
+int launch_fused(cudaStream_t s, int kernel, int grid, int nx, int ncols, const FusedArgs& args);
 // kernels_xgrad.cu
 int launch_xgrad_eval(cudaStream_t s, const GpView* gps_dev, int ngp, int tiles, const double* X_dev, int ldx, int chunk_n,
                       double* panels, double* acc);

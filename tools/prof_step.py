@@ -10,11 +10,15 @@ ap.add_argument('--config', default='C2')
 ap.add_argument('--candidates', type=int, default=None)
 ap.add_argument('--steps', type=int, default=2)
 ap.add_argument('--tri-variant', type=int, default=2)
+ap.add_argument('--option', action='append', default=[], help='name=value for gpd_set_option')
 a = ap.parse_args()
 cfg = dict(synthetic.CONFIGS[a.config])
 N = a.candidates or cfg['N']
 ctx = g.get_context(0)
 ctx.set_option('tri_variant', a.tri_variant)
+for o in a.option:
+    k, v = o.split('=')
+    ctx.set_option(k, int(v))
 models, ds = synthetic.build_models(g.GPModel, 2, cfg['M'], cfg['E'], cfg['D'], cfg['P'], cfg['n'], cfg['kernel'],
                                     build_on_device=cfg['n'] >= 2000)
 if cfg['n'] >= 2000:
