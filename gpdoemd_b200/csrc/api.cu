@@ -55,6 +55,7 @@ struct gpd_ctx {
     cudaStream_t stream2 = nullptr;         // low priority: only the evaluation overlapped with a tail wave (run_chunk)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int tail_overlap = 1;                   // option "tail_overlap"
+    int tri_parts_auto = 0, tri_parts = 0;  // option "tri_parts": 0 (default) / -1 = whole items, 9 = by factor size, 1..8 forced
     int fused = 0;                          // option "fused": first-order path through the fused evaluation + contraction kernel
     uint64_t scratch_limit = 6ull << 30;
     DevBuf scratch, tables, flush;
@@ -220,6 +221,10 @@ struct Plan {
     double *panels_in = nullptr, *panels_out = nullptr, *panels_beta = nullptr;
     int nitems = 0;
     Bump* bump = nullptr;
+    // first-order contraction units: every (GP, tile) item cut into tri_parts row-block parts of equal triangular work
+    // (large factors: the parts of a tile run on neighbouring CTAs and share its right-hand-side panel through L2)
+    Item* titems_dev = nullptr;
+    int tri_parts = 1, n_head_units = 0, n_units = 0;
     // fused evaluation + contraction (first order): no per-candidate panels, one private panel per CTA instead
     bool fused = false;
     FItem* fitems_dev = nullptr;
@@ -291,7 +296,7 @@ static int plan_build(gpd_ctx* c, gpd_model* const* models, int M, int flags, lo
             }
         // raws + hook outputs, bytes per candidate
         const int ncols = ncols_for(flags, P);
-        const int ng = pl.need_W ? nrhs * (nrhs + 1) / 2 : 8;      // first order: up to 2 row groups x 4 parts
+        const int ng = pl.need_W ? nrhs * (nrhs + 1) / 2 : 32;     // first order: up to 4 row groups x 8 parts
         size_t d = (size_t)E * (ncols + 1 + ng + ((flags & WANT_D2S2) ? npair : 0));
         d += (size_t)E * 2;
         if (flags & WANT_DMU) d += (size_t)E * P;
@@ -310,13 +315,26 @@ static int plan_build(gpd_ctx* c, gpd_model* const* models, int M, int flags, lo
         if (ncols_for(flags, grp.P) > 11 || grp.nx > kMaxXDims) pl.fused = false;
     for (auto& en : pl.entries) n_pad_max = std::max<long long>(n_pad_max, en.gp->n_pad);
     pl.priv_stride = n_pad_max * kFusedTile;      // per CTA: n_pad x tile candidates
+    // Row-block parts of the (unfused) first-order contraction (option "tri_parts", off by default).  A tile's
+    // right-hand-side panel is 8 n_pad x 128 bytes and row block I re-reads its first I + 1 k blocks: at n_pad = 4096
+    // that is 68 MB per item out of a 4 MB panel, all of it from HBM (148 private panels = 592 MB in flight).  Cutting
+    // every item into parts on neighbouring CTAs was meant to share the panel through L2; measured on B200 it is 9 %
+    // SLOWER (C5: 337 -> 370 ms, C4: 540 -> 592 ms): between two uses of a k block the whole chip streams ~1 GB
+    // through L2, so the panel is evicted either way, and the factor chunks lose their 148-way sharing
+    // (profiles/r02_summary.md).  The mechanism stays because the fused kernel cuts its tail-wave items the same way.
+    {
+        int nblk_min = 1 << 30;
+        for (auto& en : pl.entries) nblk_min = std::min(nblk_min, en.gp->nblk);
+        pl.tri_parts = (!pl.need_W && !pl.fused && c->tri_parts_auto) ? std::max(1, std::min(8, nblk_min / 4)) : 1;
+        if (c->tri_parts > 0 && !pl.need_W && !pl.fused) pl.tri_parts = std::max(1, std::min(std::min(8, nblk_min), c->tri_parts));
+    }
     // panels: in (max_nrhs kinds), out (only when W is needed), beta (only for d2s2)
     int kinds = pl.max_nrhs + (pl.need_W ? pl.max_nrhs : 0) + ((flags & WANT_D2S2) ? 1 : 0);
     pl.fixed_bytes = 0;
     if (pl.fused) {
         pl.fixed_bytes = sizeof(double) * (size_t)pl.priv_stride * kFusedCtasPerSm * c->num_sms + sizeof(FItem) * 16 * (size_t)c->num_sms + (1 << 16);
         extra_fixed += pl.fixed_bytes;
-        per_cand += (2 * sizeof(FItem) * pl.entries.size() + kBlk - 1) / kBlk; // one FItem per (GP, half tile)
+        per_cand += (2 * sizeof(FItem) * pl.entries.size() + kBlk - 1) / kBlk; // one Item per (GP, tile)
     } else per_cand += (size_t)pl.panel_unit * kinds * sizeof(double);
     pl.per_cand_bytes = per_cand;
     const size_t fixed = extra_fixed + (size_t)(1 << 20) +
@@ -424,7 +442,8 @@ static int plan_materialize(gpd_ctx* c, Plan& pl, Bump& bump) {
         const int nrhs = pl.need_W ? 1 + P : 1;
         ModelBufs& b = pl.mb[m];
         b.ldraw = ncols_for(pl.flags, P);
-        b.ng = pl.need_W ? nrhs * (nrhs + 1) / 2 : (pl.fused ? 2 * pl.fused_parts : tri_row_groups(c->tri_variant));
+        b.ng = pl.need_W ? nrhs * (nrhs + 1) / 2
+                         : (pl.fused ? 2 * pl.fused_parts : tri_row_groups(c->tri_variant) * pl.tri_parts);
         b.raw.cmu = bump.take<double>((size_t)E * Nc * b.ldraw);
         b.raw.kss = bump.take<double>((size_t)E * Nc);
         b.raw.gram = bump.take<double>((size_t)E * Nc * b.ng);
@@ -507,13 +526,25 @@ static int plan_materialize(gpd_ctx* c, Plan& pl, Bump& bump) {
     pl.head_tiles = 0;
     pl.n_head = pl.n_big = 0;
     if (c->tail_overlap && !pl.need_W && !pl.fused) {
-        const long long S = c->num_sms, G = (long long)pl.entries.size();
+        const long long S = c->num_sms, G = (long long)pl.entries.size() * pl.tri_parts;   // contraction units per tile
         long long a = S, b = G;
         while (b) { const long long t = a % b; a = b; b = t; }      // a = gcd(S, G)
         const long long period = S / a;                              // tiles per GP that make whole waves
         const long long h = pl.tiles % period;
         if (h > 0 && (long long)pl.tiles * G > S && h < pl.tiles) pl.head_tiles = (int)h;
     }
+    // contraction units of the first-order path: the items (head tiles first when the tail overlap is on) cut into parts
+    std::vector<Item> titems;
+    auto expand = [&](const std::vector<Item>& src) {
+        for (const Item& it : src) {
+            const gpd_gp* g = pl.entries[it.gp].gp;
+            if (pl.tri_parts <= 1) { titems.push_back(it); continue; }
+            const std::vector<int> bnd = split_rows(g->nblk, pl.tri_parts, 0.0);
+            const int np = (int)bnd.size() - 1;
+            for (int p = 0; p < np; ++p)
+                titems.push_back(Item{it.gp, it.tile, (short)bnd[p], (short)bnd[p + 1], (short)p, (short)np});
+        }
+    };
     if (pl.head_tiles) {
         for (int pass = 0; pass < 2; ++pass)
             for (auto& grp : pl.groups) {
@@ -526,15 +557,30 @@ static int plan_materialize(gpd_ctx* c, Plan& pl, Bump& bump) {
         pl.n_head = (int)pl.entries.size() * pl.head_tiles;
         pl.n_big = (int)items2.size() - pl.n_head;
     }
+    int n_head_units = 0;
+    if (!pl.need_W && !pl.fused) {
+        if (pl.head_tiles) {
+            expand(std::vector<Item>(items2.begin(), items2.begin() + pl.n_head));
+            n_head_units = (int)titems.size();
+            expand(std::vector<Item>(items2.begin() + pl.n_head, items2.end()));
+        } else {
+            expand(items);
+        }
+    }
+    pl.n_head_units = n_head_units;
+    pl.n_units = (int)titems.size();
     pl.views_dev = bump.take<GpView>(views.size());
     pl.items_dev = bump.take<Item>(items.size());
     pl.items2_dev = items2.empty() ? nullptr : bump.take<Item>(items2.size());
+    pl.titems_dev = titems.empty() ? nullptr : bump.take<Item>(titems.size());
     pl.raws_dev = bump.take<RawOut>(M);
     GPD_CHECK(bump.off <= bump.cap, "internal: scratch plan overflow");
     GPD_CUDA(cudaMemcpyAsync(pl.views_dev, views.data(), sizeof(GpView) * views.size(), cudaMemcpyHostToDevice, c->stream));
     GPD_CUDA(cudaMemcpyAsync(pl.items_dev, items.data(), sizeof(Item) * items.size(), cudaMemcpyHostToDevice, c->stream));
     if (pl.items2_dev)
         GPD_CUDA(cudaMemcpyAsync(pl.items2_dev, items2.data(), sizeof(Item) * items2.size(), cudaMemcpyHostToDevice, c->stream));
+    if (pl.titems_dev)
+        GPD_CUDA(cudaMemcpyAsync(pl.titems_dev, titems.data(), sizeof(Item) * titems.size(), cudaMemcpyHostToDevice, c->stream));
     GPD_CUDA(cudaMemcpyAsync(pl.raws_dev, raws.data(), sizeof(RawOut) * M, cudaMemcpyHostToDevice, c->stream));
     if (pl.fused)
         GPD_CUDA(cudaMemcpyAsync(pl.fitems_dev, fitems.data(), sizeof(FItem) * fitems.size(), cudaMemcpyHostToDevice, c->stream));
@@ -652,20 +698,21 @@ static int run_chunk(gpd_ctx* c, Plan& pl, double* X_dev, int ldx, int nc, const
         const double fh = (double)pl.n_head / (pl.n_head + pl.n_big);
         {
             Span sp(c, F_TRI_HEAD, 1, n2sum * fh);
-            GPD_TRY(launch_tri(s, pl.views_dev, pl.items2_dev, pl.n_head, 1, 1, 1, 0, pl.panels_in, nullptr, pl.raws_dev,
-                               tri_row_groups(c->tri_variant), nc, c->num_sms, c->tri_variant, tri_cps_for(c, pl), c->tri_trim));
+            GPD_TRY(launch_tri(s, pl.views_dev, pl.titems_dev, pl.n_head_units, 1, 1, 1, 0, pl.panels_in, nullptr, pl.raws_dev,
+                               tri_row_groups(c->tri_variant) * pl.tri_parts, nc, c->num_sms, c->tri_variant, tri_cps_for(c, pl), c->tri_trim));
         }
         GPD_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
         Span sp(c, F_TRI, 1, n2sum * (1.0 - fh));
-        GPD_TRY(launch_tri(s, pl.views_dev, pl.items2_dev + pl.n_head, pl.n_big, 1, 1, 1, 0, pl.panels_in, nullptr, pl.raws_dev,
-                           tri_row_groups(c->tri_variant), nc, c->num_sms, c->tri_variant, tri_cps_for(c, pl), c->tri_trim));
+        GPD_TRY(launch_tri(s, pl.views_dev, pl.titems_dev + pl.n_head_units, pl.n_units - pl.n_head_units, 1, 1, 1, 0, pl.panels_in,
+                           nullptr, pl.raws_dev, tri_row_groups(c->tri_variant) * pl.tri_parts, nc, c->num_sms, c->tri_variant,
+                           tri_cps_for(c, pl), c->tri_trim));
     } else
     if (pl.fused) {
         // evaluation and contraction already ran in the fused launch above
     } else if (!pl.need_W) {
         Span sp(c, F_TRI, 1, n2sum);
-        GPD_TRY(launch_tri(s, pl.views_dev, pl.items_dev, pl.nitems, 1, 1, 1, 0, pl.panels_in, nullptr, pl.raws_dev,
-                           tri_row_groups(c->tri_variant), nc, c->num_sms, c->tri_variant, tri_cps_for(c, pl),
+        GPD_TRY(launch_tri(s, pl.views_dev, pl.titems_dev, pl.n_units, 1, 1, 1, 0, pl.panels_in, nullptr, pl.raws_dev,
+                           tri_row_groups(c->tri_variant) * pl.tri_parts, nc, c->num_sms, c->tri_variant, tri_cps_for(c, pl),
                            c->tri_trim));
     } else {
         for (auto& grp : pl.groups) {
@@ -825,6 +872,12 @@ int gpd_set_option(gpd_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "tail_overlap")) {
         GPD_CHECK(value == 0 || value == 1, "tail_overlap is 0 or 1");
         c->tail_overlap = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "tri_parts")) {
+        GPD_CHECK(value >= -1 && value <= 9, "tri_parts is 0 / -1 (whole items), 1..8, or 9 (by factor size)");
+        c->tri_parts_auto = value == 9;
+        c->tri_parts = (value > 0 && value < 9) ? (int)value : 0;
         return 0;
     }
     if (!strcmp(name, "fused")) {
@@ -1380,7 +1433,7 @@ static int hooks_host(gpd_model* mo, const double* X, int64_t N, int flags, cons
     const int D = mo->D, E = mo->E, P = mo->P;
     GPD_TRY(plan_build(c, &mo, 1, flags, N, sizeof(double) * D, 0, pl));
     const size_t total = pl.per_cand_bytes * ((size_t)pl.chunk + kBlk) + (8u << 20) + pl.fixed_bytes + pl.entries.size() * sizeof(GpView) +
-                         (size_t)pl.entries.size() * pl.tiles * sizeof(Item) * 2;
+                         (size_t)pl.entries.size() * pl.tiles * sizeof(Item) * 10;
     GPD_TRY(ensure_scratch(c, total));
     Bump bump(c->scratch.p, c->scratch.cap);
     double* X_dev = bump.take<double>((size_t)pl.chunk * D);
@@ -1469,7 +1522,7 @@ int gpd_marginal(gpd_model* mo, const double* X, int64_t N, int order, double* m
     const size_t extra = sizeof(double) * ((size_t)D + (size_t)E * E + (order == 2 ? (size_t)E * P * P + E : 0));
     GPD_TRY(plan_build(c, &mo, 1, order_flags(order), N, extra, 0, pl));
     const size_t total = pl.per_cand_bytes * ((size_t)pl.chunk + kBlk) + (8u << 20) + pl.fixed_bytes + pl.entries.size() * sizeof(GpView) +
-                         (size_t)pl.entries.size() * pl.tiles * sizeof(Item) * 2;
+                         (size_t)pl.entries.size() * pl.tiles * sizeof(Item) * 10;
     GPD_TRY(ensure_scratch(c, total));
     Bump bump(c->scratch.p, c->scratch.cap);
     double* X_dev = bump.take<double>((size_t)pl.chunk * D);
@@ -1690,7 +1743,7 @@ static int score_impl(gpd_ctx* c, gpd_model* const* models, int32_t M, const dou
         if (order == 2) extra += sizeof(double) * ((size_t)E * maxP * maxP + E);
         GPD_TRY(plan_build(c, models, M, order_flags(order), N, extra, 0, pl));
         const size_t total = pl.per_cand_bytes * ((size_t)pl.chunk + kBlk) + (8u << 20) + pl.fixed_bytes + pl.entries.size() * sizeof(GpView) +
-                             (size_t)pl.entries.size() * pl.tiles * sizeof(Item) * 2;
+                             (size_t)pl.entries.size() * pl.tiles * sizeof(Item) * 10;
         GPD_TRY(ensure_scratch(c, total));
         Bump bump(c->scratch.p, c->scratch.cap);
         const int Nc0 = pl.chunk;
@@ -2008,7 +2061,7 @@ int gpd_marginals(gpd_ctx* c, gpd_model* const* models, int32_t M, const double*
     if (order == 2) extra += sizeof(double) * ((size_t)E * maxP * maxP + E);
     int rc = plan_build(c, models, M, order_flags(order), N, extra, 0, pl);
     const size_t total = pl.per_cand_bytes * ((size_t)pl.chunk + kBlk) + (8u << 20) + pl.fixed_bytes + pl.entries.size() * sizeof(GpView) +
-                         (size_t)pl.entries.size() * pl.tiles * sizeof(Item) * 2;
+                         (size_t)pl.entries.size() * pl.tiles * sizeof(Item) * 10;
     if (!rc) rc = ensure_scratch(c, total);
     if (rc) {
         gpd_resident_free(res);

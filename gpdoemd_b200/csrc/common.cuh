@@ -42,7 +42,11 @@ struct GpView {
 };
 
 // Work item of the evaluation / triangular kernels: GP + candidate tile (128 columns).
-struct Item { int gp; int tile; };
+// I0 / I1: row blocks [I0, I1) of the triangular contraction this unit covers; I1 == 0 means all of them (the value an
+// `Item{gp, tile}` initialiser leaves).  The units of one (GP, tile) that is cut into parts publish their ||v||^2
+// partials in distinct slots (part * row groups + row group) and, scheduled on neighbouring CTAs, share the tile's
+// right-hand-side panel through L2 instead of re-reading it from HBM once per row block.
+struct Item { int gp; int tile; short I0, I1; short part, nparts; };
 
 // Fused evaluation + contraction kernel (fused_impl.cuh): candidates per work item and CTAs per SM.  128 / 1 = one
 // 512-thread CTA per SM (3 x 32 k pipeline stages); 64 / 2 = two 256-thread CTAs per SM on half tiles (4 x 16 k), which
@@ -55,7 +59,7 @@ constexpr int kFusedCtasPerSm = kBlk / kFusedTile;
 
 // Work item of the fused evaluation + contraction kernel: row blocks [I0, I1) of (GP, tile); the parts of one (GP, tile)
 // write their ||v||^2 partials to distinct slots
-struct FItem { int gp; int tile; short I0, I1; short part, nparts; };
+typedef Item FItem;
 
 // Per-model raw outputs for a chunk (device pointers), transformed units.
 struct RawOut {

@@ -211,19 +211,20 @@ __global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) fused_kernel(c
         const int count = g.count ? *g.count : args.chunk_n;
         if (it.tile * kFusedTile >= count) continue;       // uniform over the CTA
         const int nblk = g.nblk;
+        const int I0 = it.I0, I1 = it.I1 ? it.I1 : nblk;
         // ===== evaluation: panel rows [0, I1 * 128) =====
-        fused_eval<KERN, NXB, NCB>(g, args, it.tile, count, it.I1 * kBlk, it.I1 == nblk, panel, scratch, fs.tab);
+        fused_eval<KERN, NXB, NCB>(g, args, it.tile, count, I1 * kBlk, I1 == nblk, panel, scratch, fs.tab);
         // the panel was written through the generic proxy and is read back by bulk async copies
         asm volatile("fence.proxy.async;" ::: "memory");
         __syncthreads();
         // ===== contraction: row blocks [I0, I1) =====
         if (is_producer) {
-            ps.j = (int)tile_run_base(nblk, it.I0, 0) * kChunksPerBlk;
-            ps.jend = (int)tile_run_base(nblk, it.I1, 0) * kChunksPerBlk;
-            ps.I = it.I0;
+            ps.j = (int)tile_run_base(nblk, I0, 0) * kChunksPerBlk;
+            ps.jend = (int)tile_run_base(nblk, I1, 0) * kChunksPerBlk;
+            ps.I = I0;
             ps.q = 0;
             ps.c = 0;
-            ps.len = it.I0 + 1;
+            ps.len = I0 + 1;
             ps.A = g.LinvF;
             ps.B = panel;
 #pragma unroll 1
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) fused_kernel(c
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) csq[nb][0] = csq[nb][1] = 0.0;
 #pragma unroll 1
-        for (int I = it.I0; I < it.I1; ++I) {
+        for (int I = I0; I < I1; ++I) {
             double acc[MB][NB][2];
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb)

@@ -43,12 +43,13 @@ __device__ __forceinline__ void stream_seek_item(ChunkStream& ps, const TriArgs&
         ps.A = BWD ? g.LinvB : g.LinvF;
         ps.B = args.panels_in + (args.in_stride == 1 ? g.panel_off : g.panel_off_w) +
                ((size_t)(it.tile * args.in_stride + a) * g.n_pad) * kBlk;
-        ps.total = (int)packed_tiles(g.nblk) * kChunksPerBlk;
-        ps.j = 0;
-        ps.I = 0;
+        const int I0 = it.I0, I1 = it.I1 ? it.I1 : g.nblk;
+        ps.total = (int)tile_run_base(g.nblk, I1, BWD) * kChunksPerBlk;
+        ps.j = (int)tile_run_base(g.nblk, I0, BWD) * kChunksPerBlk;
+        ps.I = I0;
         ps.q = 0;
         ps.c = 0;
-        ps.len = tile_run_len(g.nblk, 0, BWD);
+        ps.len = tile_run_len(g.nblk, I0, BWD);
         return;
     }
 }
@@ -140,8 +141,9 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) tri_kernel(const TriArgs args
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) csq[nb][0] = csq[nb][1] = 0.0;
 
+        const int I0 = it.I0, I1 = it.I1 ? it.I1 : nblk;
 #pragma unroll 1
-        for (int I = 0; I < nblk; ++I) {
+        for (int I = I0; I < I1; ++I) {
             double acc[MB][NB][2];
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb)
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) tri_kernel(const TriArgs args
                 if (slot < count) {
                     const int cand = g.idx ? g.idx[slot] : slot;
                     const RawOut& raw = args.raws[g.model];
-                    raw.gram[((size_t)g.out_e * args.chunk_n + cand) * args.ng + wm] = mine;
+                    raw.gram[((size_t)g.out_e * args.chunk_n + cand) * args.ng + it.part * WM + wm] = mine;
                 }
             }
         }
