@@ -92,7 +92,12 @@ int  gpd_set_scratch_bytes(gpd_ctx* ctx, uint64_t bytes);
  * "tri_cps" 0 = automatic, 1 = 4 pipeline stages of 16 k, 2 = 3 stages of 32 k;
  * "tail_overlap" 1 (default) = first-order path: the candidate tiles that would form the last, partial wave of the
  *   persistent triangular kernel are evaluated and contracted first, concurrently with the evaluation of the rest;
- * "tri_trim" 1 (default) = the all-padding 8-row blocks (rows n..n_pad) of the last row block are skipped */
+ * "tri_trim" 1 (default) = the all-padding 8-row blocks (rows n..n_pad) of the last row block are skipped;
+ * "fused" 0 (default) / 1 = first-order path through ONE persistent kernel that evaluates the kernel rows into a private
+ *   L2-resident panel and contracts them in place: O(SMs * n) scratch instead of O(N * n), measured 1-8 % slower than the
+ *   separate kernels;
+ * "tri_parts" 0 (default) = whole work items, 1..8 = every (GP, tile) item of the first-order contraction cut into that
+ *   many row-block parts, 9 = by factor size (measured slower at n = 4000, kept for experiments) */
 int  gpd_set_option(gpd_ctx* ctx, const char* name, int64_t value);
 /* number of CUDA kernels launched by this context so far (bench.py `gpu_launches`) */
 uint64_t gpd_launch_count(gpd_ctx* ctx);
