@@ -55,6 +55,7 @@ struct gpd_ctx {
     cudaStream_t stream2 = nullptr;         // low priority: only the evaluation overlapped with a tail wave (run_chunk)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int tail_overlap = 1;                   // option "tail_overlap"
+    int head_periods = 0, head_grid = 0;    // options "head_periods" / "head_grid": see plan_materialize (tail overlap)
     int tri_parts_auto = 0, tri_parts = 0;  // option "tri_parts": 0 (default) / -1 = whole items, 9 = by factor size, 1..8 forced
     int fused = 0;                          // option "fused": first-order path through the fused evaluation + contraction kernel
     uint64_t scratch_limit = 6ull << 30;
@@ -85,7 +86,7 @@ struct gpd_ctx {
 
 struct gpd_gp {
     gpd_ctx* ctx = nullptr;
-    int kernel = 0, n = 0, n_pad = 0, nblk = 0, D = 0, P = 0, nx = 0;
+    int kernel = 0, n = 0, n_pad = 0, nblk = 0, D = 0, P = 0, nx = 0, factor_kind = 0;
     int x_active[kMaxXDims];
     double ls_x[kMaxXDims];
     double var_x = 1, var_p = 1, power_x = 2, power_p = 2;
@@ -532,6 +533,13 @@ static int plan_materialize(gpd_ctx* c, Plan& pl, Bump& bump) {
         const long long period = S / a;                              // tiles per GP that make whole waves
         const long long h = pl.tiles % period;
         if (h > 0 && (long long)pl.tiles * G > S && h < pl.tiles) pl.head_tiles = (int)h;
+        // option "head_periods": a LONGER head (+ k whole-wave periods of tiles) whose triangular launch, restricted to
+        // "head_grid" CTAs, keeps part of the SMs on the tensor pipe for the whole evaluation of the rest (which is bound
+        // by its panel write and tolerates fewer SMs)
+        if (c->head_periods > 0 && (long long)pl.tiles * G > S) {
+            const long long want = h + (long long)c->head_periods * period;
+            if (want > 0 && want < pl.tiles) pl.head_tiles = (int)want;
+        }
     }
     // contraction units of the first-order path: the items (head tiles first when the tail overlap is on) cut into parts
     std::vector<Item> titems;
@@ -699,7 +707,9 @@ static int run_chunk(gpd_ctx* c, Plan& pl, double* X_dev, int ldx, int nc, const
         {
             Span sp(c, F_TRI_HEAD, 1, n2sum * fh);
             GPD_TRY(launch_tri(s, pl.views_dev, pl.titems_dev, pl.n_head_units, 1, 1, 1, 0, pl.panels_in, nullptr, pl.raws_dev,
-                               tri_row_groups(c->tri_variant) * pl.tri_parts, nc, c->num_sms, c->tri_variant, tri_cps_for(c, pl), c->tri_trim));
+                               tri_row_groups(c->tri_variant) * pl.tri_parts, nc,
+                               c->head_grid > 0 ? std::min(c->head_grid, c->num_sms) : c->num_sms, c->tri_variant,
+                               tri_cps_for(c, pl), c->tri_trim));
         }
         GPD_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
         Span sp(c, F_TRI, 1, n2sum * (1.0 - fh));
@@ -872,6 +882,16 @@ int gpd_set_option(gpd_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "tail_overlap")) {
         GPD_CHECK(value == 0 || value == 1, "tail_overlap is 0 or 1");
         c->tail_overlap = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "head_periods")) {
+        GPD_CHECK(value >= 0 && value <= 16, "head_periods is 0..16");
+        c->head_periods = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "head_grid")) {
+        GPD_CHECK(value >= 0 && value <= 1024, "head_grid is 0 (all SMs) or a CTA count");
+        c->head_grid = (int)value;
         return 0;
     }
     if (!strcmp(name, "tri_parts")) {
@@ -1169,6 +1189,7 @@ int gpd_gp_upload(gpd_ctx* c, const gpd_gp_desc* d, gpd_gp** out) {
     GPD_CHECK(d->alpha && d->L, "null array in descriptor");
     gpd_gp* g = nullptr;
     GPD_TRY(gp_create_common(c, d, &g));
+    g->factor_kind = d->factor_kind;
     const int n = g->n;
     cudaStream_t s = c->stream;
     double* L_dev = nullptr;
@@ -1404,6 +1425,9 @@ static int upload_model_state(gpd_model* mo) {
         xf[1].pdiff[a] = 1.0;
     }
     for (int k = 0; k < P * P; ++k) xf[0].Sigma[k] = xf[1].Sigma[k] = mo->Sigma[k];
+    bool sparse = false;
+    for (gpd_gp* g : mo->gps) sparse = sparse || (g && g->factor_kind == GPD_FACTOR_ROOT);
+    xf[0].var_floor = xf[1].var_floor = sparse ? 1e-15 : -HUGE_VAL;
     cudaStream_t s = c->stream;
     GPD_CUDA(cudaMemcpyAsync(mo->xf_dev, xf, sizeof(xf), cudaMemcpyHostToDevice, s));
     GPD_CUDA(cudaMemcpyAsync(mo->pstar_dev, mo->pstar.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));

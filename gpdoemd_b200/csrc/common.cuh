@@ -74,6 +74,8 @@ struct ModelXform {              // device copy of the per-model unit conversion
     double ymean[kMaxE], ystd[kMaxE];
     double pdiff[kMaxP];
     double Sigma[kMaxP * kMaxP]; // row-major, stride P
+    double var_floor;            // lower clip of the predictive variance in transformed units: 1e-15 for sparse GPs
+                                 // (GPy's base Posterior._raw_predict clips), -inf for exact GPs (PosteriorExact does not)
 };
 
 struct PostModel {               // per model slot of a fused scoring call (device table)

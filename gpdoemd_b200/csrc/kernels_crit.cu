@@ -62,7 +62,7 @@ __global__ void finalize_kernel(const ModelXform* __restrict__ xf, const RawOut*
     double vv = gr[0];
     for (int k = 1; k < npart; ++k) vv += gr[k];
     mu[(size_t)n * ldmu + e] = xf->ymean[e] + c[0] * ystd;                // transform.py:69-73 back=True
-    s2[(size_t)n * E + e] = (raw.kss[row] - vv) * (ystd * ystd);      // k** - v'v  (GPy _raw_predict)
+    s2[(size_t)n * E + e] = fmax(raw.kss[row] - vv, xf->var_floor) * (ystd * ystd);   // k** - v'v  (GPy _raw_predict)
     if (flags & 1) {                                                     // d_mu_d_p  surrogate_model.py:185-189
         double* o = dmu + ((size_t)n * E + e) * P;
         for (int a = 0; a < P; ++a) o[a] = c[1 + a] * ystd / xf->pdiff[a];
@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(128) post1_kernel(const PostModel* __restrict_
         double vv = gr[0];
         for (int k = 1; k < pm.npart; ++k) vv += gr[k];
         w.mu[((size_t)m * E + e) * N + n] = xf->ymean[e] + c[0] * ystd;
-        s2[e] = (raw.kss[row] - vv) * (ystd * ystd);
+        s2[e] = fmax(raw.kss[row] - vv, xf->var_floor) * (ystd * ystd);
         for (int a = 0; a < P; ++a) J[e][a] = c[1 + a] * ystd / xf->pdiff[a];
     }
     double A[E][E];

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(128) xgrad_finalize_kernel(const XgradArgs a) 
         const double* c = a.acc + ((size_t)gi * a.chunk_n + n) * (size_t)(nk * ncol);
         const double* gr = a.gram + ((size_t)gi * a.chunk_n + n) * a.ngram;
         a.mu[(size_t)n * E + e] = xf->ymean[e] + c[0] * ystd;
-        s2[e] = (g.kss - gr[0]) * (ystd * ystd);
+        s2[e] = fmax(g.kss - gr[0], xf->var_floor) * (ystd * ystd);
         for (int p = 0; p < P; ++p) J[e][p] = c[1 + p] * ystd / xf->pdiff[p];
         for (int d = 0; d < D; ++d) a.dmu[((size_t)n * E + e) * D + d] = 0.0;
         for (int d = 0; d < nx; ++d) {

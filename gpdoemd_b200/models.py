@@ -477,10 +477,16 @@ class GPModel:
         f = _lib.as_f64
         xmin, xmax, pmin, pmax = f(self.xmin), f(self.xmax), f(self.pmin), f(self.pmax)
         ymean, ystd = f(self.ymean), f(self.ystd)
-        check(ctx.lib.gpd_model_create(ctx.handle, E, self.dim_x, self.dim_p, len(bv),
-                                       bv.ctypes.data_as(_lib.c_int32_p) if len(bv) else None,
-                                       C.cast(handles, _lib.c_void_pp), dptr(xmin), dptr(xmax), dptr(pmin),
-                                       dptr(pmax), dptr(ymean), dptr(ystd), C.byref(mh)))
+        try:
+            check(ctx.lib.gpd_model_create(ctx.handle, E, self.dim_x, self.dim_p, len(bv),
+                                           bv.ctypes.data_as(_lib.c_int32_p) if len(bv) else None,
+                                           C.cast(handles, _lib.c_void_pp), dptr(xmin), dptr(xmax), dptr(pmin),
+                                           dptr(pmax), dptr(ymean), dptr(ystd), C.byref(mh)))
+        except Exception:
+            for h in self._dev_gps:            # a refused model (size limit) must not leak its uploaded GPs
+                ctx.lib.gpd_gp_free(h)
+            self._dev_gps = []
+            raise
         self._dev_model = mh
 
     def _sync_device(self, pstar=None):

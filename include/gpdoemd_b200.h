@@ -96,6 +96,8 @@ int  gpd_set_scratch_bytes(gpd_ctx* ctx, uint64_t bytes);
  * "fused" 0 (default) / 1 = first-order path through ONE persistent kernel that evaluates the kernel rows into a private
  *   L2-resident panel and contracts them in place: O(SMs * n) scratch instead of O(N * n), measured 1-8 % slower than the
  *   separate kernels;
+ * "head_periods" 0 (default) .. 16 / "head_grid" 0 (all SMs) or a CTA count: a longer tail-overlap head on a restricted
+ *   grid (measured neutral on C2);
  * "tri_parts" 0 (default) = whole work items, 1..8 = every (GP, tile) item of the first-order contraction cut into that
  *   many row-block parts, 9 = by factor size (measured slower at n = 4000, kept for experiments) */
 int  gpd_set_option(gpd_ctx* ctx, const char* name, int64_t value);

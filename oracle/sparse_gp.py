@@ -92,7 +92,10 @@ class SparseGPRegression(GPRegression):
             Kx = self.kern.K(self._predictive_variable, Xc)
             mu[s:s + chunk] = np.dot(Kx.T, self.posterior.woodbury_vector)
             var[s:s + chunk, 0] = self.kern.Kdiag(Xc) - np.sum(np.dot(W.T, Kx) * Kx, 0)
-        return mu, var
+        # GPy's base Posterior._raw_predict (the class SparseGPRegression uses) ends its full_cov=False branch with
+        # `var = np.clip(var, 1e-15, np.inf)`; PosteriorExact (exact GPRegression, gp.py) does not.  Restated from
+        # memory of GPy 1.9.x like the rest of this module: parity with real GPy is unpinned.
+        return mu, np.clip(var, 1e-15, np.inf)
 
 
 def _jitchol(A):

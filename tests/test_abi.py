@@ -98,3 +98,22 @@ def test_binary_combo_weights_match_reference_order():
         w = [lib.gpd_binary_combo_weight(nb, v) for v in range(nb)]
         for j, row in enumerate(B):
             assert sum(wv for wv, s in zip(w, row) if s > 0) == j
+
+
+def test_header_is_valid_c(tmp_path):
+    """include/gpdoemd_b200.h is the boundary a C / cgo / JNI host would bind: it must compile as plain C99 and C++17."""
+    import subprocess
+    src = tmp_path / 'use_header.c'
+    src.write_text('#include "gpdoemd_b200.h"\n'
+                   'int probe(gpd_ctx* c, gpd_comm* k, gpd_model* const* m, const double* x, double* bv, int64_t* bi) {\n'
+                   '    const int32_t kinds[2] = {GPD_HR, GPD_BH};\n'
+                   '    char id[GPD_NCCL_ID_BYTES];\n'
+                   '    double noise[4] = {0.01, 0, 0, 0.01}, pps[2] = {0.5, 0.5};\n'
+                   '    if (gpd_nccl_unique_id(id)) return 1;\n'
+                   '    return gpd_score_sharded(c, k, m, 2, x, 0, 100, 1, kinds, 2, noise, pps, 0, 0, bv, bi, 0) == GPD_ERR_SINGULAR;\n'
+                   '}\n')
+    inc = os.path.join(ROOT, 'include')
+    for cmd in (['gcc', '-std=c99', '-Wall', '-Werror', '-pedantic', '-I', inc, '-c', str(src), '-o', str(tmp_path / 'a.o')],
+                ['g++', '-std=c++17', '-Wall', '-Werror', '-x', 'c++', '-I', inc, '-c', str(src), '-o', str(tmp_path / 'b.o')]):
+        out = subprocess.run(cmd, capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr

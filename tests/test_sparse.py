@@ -134,3 +134,28 @@ def test_sparse_model_built_by_the_product(gpu_ctx):
     assert helpers.relerr(M1, M0, oms[0].ystd) < 1e-8
     assert helpers.relerr(S1, S0, vs) < 1e-8          # against the prior variance: sigma^2 itself is ~1e-5 of it here
     assert gms[0].max_num_inducing == 500
+
+
+@pytest.mark.gpu
+def test_sparse_variance_floor_like_gpys_base_posterior(gpu_ctx):
+    """GPy's base Posterior._raw_predict (SparseGPRegression) clips the predictive variance at 1e-15 in
+    standardised units, PosteriorExact (exact GPs) does not.  The device applies the same floor to GPD_FACTOR_ROOT
+    models only.  A sparse posterior whose woodbury_inv overshoots (k** - k^T W k < 0 at the inducing inputs) shows it;
+    an exact model with the same numbers keeps the negative value."""
+    import gpdoemd_b200 as g
+    oms, ds = helpers.oracle_sparse_models(13, M=1, E=1, D=2, P=2, n=120, kernel='RBF', num_inducing=40)
+    om = oms[0]
+    gp = om.gps[0][0]
+    gp.posterior.woodbury_inv = gp.posterior.woodbury_inv * (1.0 + 1e-3)      # overshoot: variances go slightly negative
+    gm = g.SparseGPModel.from_reference(om)
+    Zt = gp._predictive_variable                                                # the inducing inputs, transformed units
+    om.pmean = om.trans_p(Zt[7, 2:], back=True)
+    gm.pmean = om.pmean.copy()
+    X = om.trans_x(Zt[:30, :2], back=True)
+    M0, S0 = om.predict(X)
+    M1, S1 = gm.predict(X)
+    floor = 1e-15 * om.ystd ** 2
+    assert np.any(S0 == floor) and np.all(S0 >= floor)          # the oracle (GPy's clip) bites on this input
+    assert np.all(S1 >= floor)
+    vs = gp.kern.kernx.variance * gp.kern.kernp.variance * om.ystd ** 2
+    assert helpers.relerr(S1, S0, vs) < 1e-8 and np.array_equal(S1 == floor, S0 == floor)
