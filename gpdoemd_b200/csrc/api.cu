@@ -81,6 +81,9 @@ struct gpd_ctx {
     // copies cost ~0.1 ms per call (1.5 % of a C2 step).  Any other use of the scratch region, a freed handle or a
     // changed option invalidates it.
     struct ScoreState* score_state = nullptr;
+    // device buffers of freed resident marginals, kept for the next gpd_marginals call (a design loop asks for the same
+    // sizes over and over; cudaMalloc + cudaFree per call cost ~0.5 ms and cudaFree synchronises the device)
+    std::vector<std::pair<void*, size_t>> res_pool;
     uint64_t epoch = 1;                     // bumped by everything that invalidates cached plans
 };
 
@@ -834,6 +837,7 @@ void gpd_destroy(gpd_ctx* c) {
     c->scratch.release();
     c->tables.release();
     c->flush.release();
+    for (auto& e : c->res_pool) cudaFree(e.first);
     for (auto& s : c->spans) {
         cudaEventDestroy(s.a);
         cudaEventDestroy(s.b);
@@ -2037,12 +2041,38 @@ struct gpd_resident {
 
 extern "C" {
 
+static void res_pool_put(gpd_ctx* c, void* p, size_t bytes) {
+    if (!p) return;
+    size_t held = bytes;
+    for (auto& e : c->res_pool) held += e.second;
+    if (c->res_pool.size() >= 8 || held > (4ull << 30)) {
+        cudaFree(p);
+        return;
+    }
+    c->res_pool.push_back({p, bytes});
+}
+static void* res_pool_take(gpd_ctx* c, size_t bytes) {
+    for (size_t i = 0; i < c->res_pool.size(); ++i)
+        if (c->res_pool[i].second == bytes) {
+            void* p = c->res_pool[i].first;
+            c->res_pool.erase(c->res_pool.begin() + i);
+            return p;
+        }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        for (auto& e : c->res_pool) cudaFree(e.first);     // make room and retry once
+        c->res_pool.clear();
+        if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+    }
+    return p;
+}
+
 void gpd_resident_free(gpd_resident* r) {
     if (!r) return;
     cudaSetDevice(r->ctx->device);
     cudaStreamSynchronize(r->ctx->stream);
-    cudaFree(r->mu_dev);
-    cudaFree(r->S_dev);
+    res_pool_put(r->ctx, r->mu_dev, sizeof(double) * (size_t)r->N * r->M * r->E);
+    res_pool_put(r->ctx, r->S_dev, sizeof(double) * (size_t)r->N * r->M * r->E * r->E);
     delete r;
 }
 
@@ -2071,10 +2101,10 @@ int gpd_marginals(gpd_ctx* c, gpd_model* const* models, int32_t M, const double*
         res->N = N;
         res->M = M;
         res->E = E;
-        cudaError_t e = cudaMalloc(&res->mu_dev, sizeof(double) * (size_t)N * M * E);
-        if (e == cudaSuccess) e = cudaMalloc(&res->S_dev, sizeof(double) * (size_t)N * M * E * E);
-        if (e != cudaSuccess) {
-            set_error(std::string("resident marginals: ") + cudaGetErrorString(e));
+        res->mu_dev = (double*)res_pool_take(c, sizeof(double) * (size_t)N * M * E);
+        res->S_dev = (double*)res_pool_take(c, sizeof(double) * (size_t)N * M * E * E);
+        if (!res->mu_dev || !res->S_dev) {
+            set_error("resident marginals: out of device memory");
             gpd_resident_free(res);
             return 1;
         }
