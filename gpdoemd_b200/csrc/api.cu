@@ -2373,14 +2373,20 @@ int gpd_score_sharded(gpd_ctx* c, gpd_comm* cm, gpd_model* const* models, int32_
     NcclApi* api = nccl_api();
     GPD_CHECK(api, "libnccl.so.2 cannot be loaded");
     GPD_CUDA(cudaSetDevice(c->device));
-    if (N_local > 0)
-        GPD_TRY(score_impl(c, models, M, X, x_on_device != 0, N_local, order, kinds, nkinds, noise, pps, dc_out,
-                           dc_on_device != 0, nullptr, nullptr, idx_offset, false));
+    // A rank whose local scoring fails still takes part in the collective (as an empty shard) so that its peers do not
+    // hang in the all-gather; it reports its own error afterwards.
+    int local_rc = 0;
+    std::string local_err;
+    if (N_local > 0) {
+        local_rc = score_impl(c, models, M, X, x_on_device != 0, N_local, order, kinds, nkinds, noise, pps, dc_out,
+                              dc_on_device != 0, nullptr, nullptr, idx_offset, false);
+        if (local_rc) local_err = g_error;
+    }
     cudaStream_t s = c->stream;
     const size_t bytes = best_pair_bytes() * (size_t)nkinds;
     {
         Span sp(c, F_COMM, 2, 0);
-        GPD_TRY(launch_best_pack(s, c->best_val_dev, c->best_idx_dev, nkinds, N_local == 0, cm->send_dev));
+        GPD_TRY(launch_best_pack(s, c->best_val_dev, c->best_idx_dev, nkinds, N_local == 0 || local_rc != 0, cm->send_dev));
         GPD_NCCL(api, api->AllGather(cm->send_dev, cm->recv_dev, bytes, ncclUint8, cm->comm, s));
         GPD_TRY(launch_best_reduce(s, cm->recv_dev, cm->world, nkinds, c->best_val_dev, c->best_idx_dev));
     }
@@ -2390,6 +2396,10 @@ int gpd_score_sharded(gpd_ctx* c, gpd_comm* cm, gpd_model* const* models, int32_
     GPD_CUDA(cudaMemcpyAsync(bi, c->best_idx_dev, sizeof(long long) * nkinds, cudaMemcpyDeviceToHost, s));
     GPD_TRY(singular_fetch(c));
     GPD_CUDA(cudaStreamSynchronize(s));
+    if (local_rc) {
+        set_error(local_err);
+        return local_rc;
+    }
     GPD_TRY(singular_rc(c));
     for (int k = 0; k < nkinds; ++k) {
         if (best_val) best_val[k] = bv[k];

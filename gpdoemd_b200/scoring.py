@@ -286,8 +286,15 @@ class LibraryComm:
 
     def close(self):
         if self.handle:
-            self.ctx.lib.gpd_comm_destroy(self.handle)
+            if self.ctx.handle:                      # a closed context took the stream the communicator used with it
+                self.ctx.lib.gpd_comm_destroy(self.handle)
             self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def pack_best(vals, idxs):
