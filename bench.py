@@ -303,6 +303,21 @@ def roofline_of(cfg, N_local, steps, ms_per_step, prof, peak, traffic):
             'kernel_ms_per_step': {k: v['ms'] / steps for k, v in prof.items() if v['launches']}}
 
 
+def hbm_secondary(traffic, launch_ms):
+    """achieved HBM GB/s of the dominant launch (ncu DRAM bytes / event-timed launch) against the measured copy
+    bandwidth of this pool -- the secondary roofline, expected far below its peak because the kernel is FP64-pipe bound."""
+    if not traffic or not launch_ms:
+        return None
+    peak, src = 6552.6, 'SURVEY 8(d) hbm_gbs (MEASURED_PEAKS.json absent)'
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
+        src = 'MEASURED_PEAKS.json hbm_gbs'
+    except Exception:
+        pass
+    ach = traffic / (launch_ms * 1e-3) / 1e9
+    return {'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'peak_source': src}
+
+
 def committed_traffic(name, N):
     """DRAM bytes (read + write) of the dominant launch from the committed ncu capture of the same command, else None."""
     for f in ('r02_traffic.json', 'r01_traffic.json'):
@@ -463,6 +478,7 @@ def main():
     traffic, traffic_src = committed_traffic(args.config, N)
     roofline = roofline_of(cfg, N, args.steps, ms_per_step, prof, peak, traffic)
     roofline['traffic_source'] = traffic_src
+    roofline['hbm'] = hbm_secondary(traffic, roofline['launch_ms'])
     roofline['peak_source'] = ('FP64 mma.sync m8n8k4 register-resident probe run in this process (MEASURED_PEAKS.json '
                                'has no FP64 entry; cuBLAS DGEMM on this pool: 36.1 TFLOP/s, profiles/r01_fp64_peak.jsonl)')
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -571,6 +587,7 @@ def main():
             tr, tr_src = committed_traffic(name, ck['N'])
             rk = roofline_of(ck, ck['N'], args.extra_steps, msk, mk['prof'], peak, tr)
             rk['traffic_source'] = tr_src
+            rk['hbm'] = hbm_secondary(tr, rk['launch_ms'])
             entry = {'workload': workload_name(ck, name), 'value': ck['N'] / (msk * 1e-3), 'unit': UNIT, 'ms_per_step': msk,
                      'steps': args.extra_steps, 'warmup': 1, 'gpu_launches': mk['launches'], 'roofline': rk,
                      'e2e': {'value': ck['N'] / (mk['e2e_ms'] / args.extra_steps * 1e-3), 'unit': UNIT},

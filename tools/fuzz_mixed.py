@@ -4,6 +4,9 @@ warnings.filterwarnings('ignore')
 import numpy as np, helpers
 import gpdoemd_b200 as g
 from gpdoemd_b200 import synthetic
+import os
+for _o in filter(None, os.environ.get('GPD_OPTIONS', '').split(',')):     # e.g. GPD_OPTIONS=fused=1,tri_parts=4
+    g.get_context(0).set_option(_o.split('=')[0], int(_o.split('=')[1]))
 from oracle import criteria as ocrit, marginal as omarg
 KS = ['RBF', 'Exponential', 'Matern32', 'Matern52', 'RatQuad']
 bad = 0
