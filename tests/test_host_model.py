@@ -193,3 +193,54 @@ def test_missing_binary_combination_raises_like_the_reference():
         gm.check_routing(X)
     with pytest.raises(AttributeError):
         g.score_designs([gm], X)
+
+
+def test_from_reference_reads_gpy_shaped_objects():
+    """GPy is not importable here, so the adoption path is exercised on objects with GPy's SHAPES: hyper-parameters are
+    1-element / d-element array subclasses (paramz `Param`), the kernel classes are subclasses of subclasses named like
+    GPy's (GPdoemd.kernels.RBF(GPy.kern.RBF)), `active_dims` are integer arrays, the posterior holds an (n, 1)
+    woodbury_vector.  GPState.from_gp must extract the same plain arrays as from the oracle's objects."""
+    class Param(np.ndarray):                                    # paramz.Param is an ndarray subclass
+        def __new__(cls, v):
+            return np.atleast_1d(np.asarray(v, dtype=float)).view(cls)
+
+    class Kern:                                                 # GPy.kern.src.kern.Kern
+        pass
+
+    class Stationary(Kern):                                     # GPy.kern.src.stationary.Stationary
+        pass
+
+    class Matern52(Stationary):                                 # GPy.kern.Matern52
+        pass
+
+    GpdoemdMatern52 = type('Matern52', (Matern52,), {})         # GPdoemd.kernels.Matern52(GPy.kern.Matern52)
+
+    oms, ds = helpers.oracle_models(9, M=1, E=1, D=3, P=2, n=40, kernel='Matern52')
+    go = oms[0].gps[0][0]
+
+    def gpy_like(k):
+        o = GpdoemdMatern52()
+        o.variance, o.lengthscale = Param(k.variance), Param(k.lengthscale)
+        o.active_dims = np.asarray(k.active_dims, dtype=np.int64)
+        return o
+
+    class Prod:
+        pass
+
+    class Posterior:
+        pass
+
+    class GPRegression:
+        pass
+    gp = GPRegression()
+    gp.kern = Prod()
+    gp.kern.kernx, gp.kern.kernp = gpy_like(go.kern.kernx), gpy_like(go.kern.kernp)
+    gp.posterior = Posterior()
+    gp.posterior.woodbury_chol = np.asfortranarray(go.posterior.woodbury_chol)         # LAPACK output order
+    gp.posterior.woodbury_vector = go.posterior.woodbury_vector.copy()
+    gp._predictive_variable = go._predictive_variable
+    a, b = GPState.from_gp(gp, 3, 2), GPState.from_gp(go, 3, 2)
+    assert a.kernel == b.kernel == 'Matern52' and (a.var_x, a.var_p) == (b.var_x, b.var_p)
+    for k in ('Z', 'alpha', 'L', 'ls_x', 'ls_p', 'x_active'):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert a.L.flags['C_CONTIGUOUS'] and a.L.dtype == np.float64 and a.alpha.shape == (40,)
