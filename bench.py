@@ -11,7 +11,7 @@ The same line carries, nested inside keys the driver keeps whole:
   roofline.configs       C3 / C4 / C5 at a reduced N of >= 40 complete persistent-kernel waves each: throughput,
                          tri_kernel fraction of the FP64 peak, pipeline fraction, parity against the CPU oracle and a
                          small CPU baseline of their own (N = 1 runs only);
-  config.scaling_sweep   BASELINE configs[4] (C5) at a FIXED GLOBAL candidate count cut into contiguous blocks over
+  roofline.scaling_sweep BASELINE configs[4] (C5) at a FIXED GLOBAL candidate count cut into contiguous blocks over
                          the N ranks (strong scaling), the all-gather inside every timed step (every N);
   cpu_baseline.parity    the CPU leg's own candidate sample scored by the GPU in the same process.
 See DESIGN.md section "Measurement" for the definition of every field.
@@ -488,8 +488,10 @@ def main():
             'argmax': {c: int(res[c][0]) for c in crits}}
     if world > 1:
         line['nccl_ms_per_step'] = m['nccl_ms'] / args.steps
-        line['config']['collective'] = ('gpd_score_sharded: pack + ncclAllGather(%d x %d x 16 B) + fold on the library stream, '
-                                        'inside every timed step' % (world, len(crits)))
+        # (kept out of `config`, which is identical in both arms)
+        line['collective'] = line['roofline']['collective'] = (
+            'gpd_score_sharded: pack + ncclAllGather(%d x %d x 16 B) + fold on the library stream, inside every timed step, '
+            '%.4f ms per step' % (world, len(crits), m['nccl_ms'] / args.steps))
     if m['e2e_ms']:
         nk = len(crits)
         line['e2e'] = {'value': N * world / (m['e2e_ms'] / args.steps * 1e-3), 'unit': UNIT,
@@ -568,8 +570,8 @@ def main():
     prob.close()
 
     if sweep is not None:
-        line['config']['scaling_sweep'] = sweep
-        line['scaling_sweep'] = sweep
+        line['roofline']['scaling_sweep'] = sweep          # nested in a key the driver keeps whole; `config` stays the
+        line['scaling_sweep'] = sweep                      # same dict in both arms
 
     # ---- C3 / C4 / C5 at a reduced N (single-GPU runs only): driver-visible roofline + parity for the big configs ------
     if not args.no_extra and args.config == 'C2' and not args.candidates and world == 1:

@@ -74,5 +74,9 @@ def test_gpu_arm_fresh_line_has_every_contract_key():
         assert name in e['workload'] and e['value'] > 0
         assert 0.5 < e['roofline']['frac'] < 1.0 and 0.5 < e['roofline']['pipeline_frac'] < 1.0
         assert e['cpu_baseline']['parity']['ok'], (name, e['cpu_baseline']['parity'])
-    sw = d['config']['scaling_sweep']
+    sw = d['roofline']['scaling_sweep']
+    sys.path.insert(0, ROOT)
+    import bench
+    from gpdoemd_b200 import synthetic
+    assert d['config'] == bench.config_dict(dict(synthetic.CONFIGS['C2']), 'C2', 1)      # same dict as the reference arm
     assert sw['scaling'] == 'strong' and sw['config_id'] == 'C5' and sw['n_gpus'] == 1 and sw['value'] > 0
