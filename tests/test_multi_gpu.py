@@ -59,3 +59,38 @@ def test_multi_device_scorer_equals_one_gpu(N, gpu_ctx):
                 assert np.array_equal(many[c][2], one[c][2])
     finally:
         sc.close()
+
+
+def test_adopting_a_communicator_the_caller_owns(gpu_ctx):
+    """gpd_comm_adopt: a host that already has an ncclComm_t (here created with NCCL's own C API through ctypes) hands it
+    to the library; gpd_comm_destroy must leave it alive."""
+    import ctypes as C
+    import gpdoemd_b200 as g
+    from gpdoemd_b200 import _lib
+    from gpdoemd_b200._lib import check
+    path = _lib._preload_nccl() or 'libnccl.so.2'
+    nccl = C.CDLL(path)
+
+    class UniqueId(C.Structure):
+        _fields_ = [('internal', C.c_char * 128)]
+    uid = UniqueId()
+    assert nccl.ncclGetUniqueId(C.byref(uid)) == 0
+    import torch
+    torch.cuda.set_device(gpu_ctx.device)
+    comm = C.c_void_p()
+    nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+    assert nccl.ncclCommInitRank(C.byref(comm), 1, uid, 0) == 0
+    oms, ds = helpers.oracle_models(44, M=2, E=2, D=2, P=2, n=70, kernel='Matern32')
+    gms = helpers.gpu_models(oms)
+    X = synthetic.candidates(7, 200, 2, np.max([d['xlo'] for d in ds], axis=0), np.min([d['xhi'] for d in ds], axis=0))
+    h = C.c_void_p()
+    check(gpu_ctx.lib.gpd_comm_adopt(gpu_ctx.handle, comm, 0, 1, C.byref(h)))
+
+    class Adopted:                        # the duck type score_designs_multi(comm=...) needs
+        ctx, handle = gpu_ctx, h
+    a = g.score_designs_multi(gms, X, ['BH'], noise_var=0.02)
+    b = g.score_designs_multi(gms, X, ['BH'], noise_var=0.02, comm=Adopted)
+    assert a['BH'][0] == b['BH'][0] and np.array_equal(a['BH'][2], b['BH'][2])
+    gpu_ctx.lib.gpd_comm_destroy(h)
+    nccl.ncclCommDestroy.argtypes = [C.c_void_p]
+    assert nccl.ncclCommDestroy(comm) == 0          # still ours to destroy
