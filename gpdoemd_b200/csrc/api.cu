@@ -93,7 +93,7 @@ struct gpd_gp {
     int x_active[kMaxXDims];
     double ls_x[kMaxXDims];
     double var_x = 1, var_p = 1, power_x = 2, power_p = 2;
-    double *Xs = nullptr, *Zp = nullptr, *alpha = nullptr, *ls_p = nullptr;
+    double *Xs = nullptr, *XsE = nullptr, *Zp = nullptr, *alpha = nullptr, *ls_p = nullptr;
     double *C = nullptr, *G = nullptr, *H = nullptr;
     double *LinvF = nullptr, *LinvB = nullptr;
 };
@@ -114,7 +114,7 @@ struct gpd_model {
 namespace gpd {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-constexpr double kRbfCoordScaleHost = 0.70710678118654752440;   // == kRbfCoordScale of eval_impl.cuh
+constexpr double kRbfCoordScaleHost = kRbfCoordScale;          // common.cuh
 
 struct NvtxRange {                // RAII range, domain-less, name prefix "gpd/"
     explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
@@ -498,6 +498,7 @@ static int plan_materialize(gpd_ctx* c, Plan& pl, Bump& bump) {
             v.kss = g->var_x * g->var_p;
             v.power_x = g->power_x;
             v.Xs = g->Xs;
+            v.XsE = g->XsE;
             v.C = g->C;
             v.G = g->G;
             v.H = g->H;
@@ -1074,6 +1075,7 @@ void gpd_gp_free(gpd_gp* g) {
     cudaSetDevice(g->ctx->device);
     cudaStreamSynchronize(g->ctx->stream);
     cudaFree(g->Xs);
+    cudaFree(g->XsE);
     cudaFree(g->Zp);
     cudaFree(g->alpha);
     cudaFree(g->ls_p);
@@ -1133,14 +1135,30 @@ static int gp_create_common(gpd_ctx* c, const gpd_gp_desc* d, gpd_gp** out) {
     for (int i = 0; i < n; ++i) {
         for (int k = 0; k < nx; ++k) {
             double v = d->Z[(size_t)i * dz + d->x_active[k]] / d->ls_x[k];
-            if (d->kernel == GPD_KERN_RBF) v *= kRbfCoordScaleHost;      // see eval_impl.cuh: exp(-r^2/2) without the 1/2
+            if (d->kernel == GPD_KERN_RBF) v *= kRbfCoordScaleHost;      // see eval_impl.cuh: the squared distance in table units
             Xs[(size_t)i * nx + k] = v;
         }
         for (int a = 0; a < P; ++a) Zp[(size_t)i * P + a] = d->Z[(size_t)i * dz + g->D + a];
     }
+    // RBF: the evaluation kernel forms the squared distance in expanded form from {-2 Xs, |Xs|^2} per training row
+    std::vector<double> XsE;
+    if (d->kernel == GPD_KERN_RBF) {
+        XsE.assign((size_t)n_pad * (nx + 1), 0.0);
+        for (int i = 0; i < n; ++i) {
+            double sq = 0.0;
+            for (int k = 0; k < nx; ++k) {
+                const double v = Xs[(size_t)i * nx + k];
+                XsE[(size_t)i * (nx + 1) + k] = -2.0 * v;
+                sq = fma(v, v, sq);
+            }
+            XsE[(size_t)i * (nx + 1) + nx] = sq;
+        }
+    }
     cudaStream_t s = c->stream;
     const size_t pack_bytes = sizeof(double) * (size_t)packed_tiles(g->nblk) * kTileElems;
     cudaError_t e = cudaMalloc(&g->Xs, sizeof(double) * Xs.size());
+    if (e == cudaSuccess && !XsE.empty()) e = cudaMalloc(&g->XsE, sizeof(double) * XsE.size());
+    if (e == cudaSuccess && !XsE.empty()) e = cudaMemcpyAsync(g->XsE, XsE.data(), sizeof(double) * XsE.size(), cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMalloc(&g->Zp, sizeof(double) * Zp.size());
     if (e == cudaSuccess) e = cudaMalloc(&g->alpha, sizeof(double) * n);
     if (e == cudaSuccess) e = cudaMalloc(&g->ls_p, sizeof(double) * P);
@@ -1953,6 +1971,7 @@ int gpd_marginal_dx(gpd_model* mo, const double* X, int64_t N, double* mu_out, d
         v.kss = g->var_x * g->var_p;
         v.power_x = g->power_x;
         v.Xs = g->Xs;
+        v.XsE = g->XsE;
         v.C = g->C;
         v.G = g->G;
         v.H = g->H;

@@ -15,6 +15,9 @@ constexpr int kMaxP = 16;        // model parameters
 constexpr int kMaxE = 8;         // outputs (register-resident E x E criteria)
 constexpr int kMaxBinary = 6;
 constexpr int kMaxKinds = 5;      // criteria scored in one fused pass
+// RBF GPs keep their x-coordinates (training rows Xs and the candidate scale xscale) multiplied by sqrt(128 / ln 2): the
+// squared distance is then the argument of the exponential table in table units (eval_impl.cuh: exp_neg_tab_units)
+constexpr double kRbfCoordScale = 13.589148804608305;
 
 // Device-side view of one GP (array in global memory, indexed by work items).
 struct GpView {
@@ -22,6 +25,7 @@ struct GpView {
     double kss;                  // var_x * var_p = k(z*, z*)
     double power_x;
     const double* Xs;            // [n_pad][nx]  training x / lengthscale   (pad rows 0)
+    const double* XsE;           // RBF only: [n_pad][nx + 1] = {-2 Xs, |Xs|^2}, the expanded-form record of eval_kernel
     const double* C;             // [1+P+P(P+1)/2][n_pad] alpha*var_x*{kp, dkp/dp_a, d2kp/dp_a dp_b (a<=b)}
     const double* G;             // [1+P][n_pad]          var_x*{kp, dkp/dp_a}          (pad rows 0)
     const double* H;             // [P(P+1)/2][n_pad]     var_x*d2kp/dp_a dp_b

@@ -43,13 +43,30 @@ __device__ __forceinline__ double exp_neg_fast(double s, const double* __restric
     return (hs - 0x4085E000u <= 0x7FF00000u - 0x4085E000u) ? 0.0 : v;
 }
 
-// The RBF profile exp(-r^2/2) is evaluated on coordinates pre-scaled by sqrt(1/2) (training rows at upload,
-// candidates when they are loaded), so the kernel loop has no multiply by -0.5.
-constexpr double kRbfCoordScale = 0.70710678118654752440;
+// The RBF profile exp(-r^2/2) is evaluated on coordinates pre-scaled by sqrt(128 / ln 2) (training rows at upload,
+// candidates when they are loaded, kRbfCoordScale in common.cuh): the squared distance then IS the table argument
+// t = (r^2 / 2) * 256 / ln 2, and the range reduction needs no multiply at all:
+//   m = -round(t) (magic add), d = t - round(t) in [-1/2, 1/2] (exact), e^-s = 2^(m>>8) * 2^((m&255)/256) * e^(-d ln2/256)
+// with the degree-4 polynomial in d (coefficients (-ln2/256)^k / k!, truncation < 4e-17): 3 DADD + 4 DFMA + 1 DMUL.
+__device__ __forceinline__ double exp_neg_tab_units(double t, const double* __restrict__ tab) {
+    const double kMagic = 6755399441055744.0;          // 1.5 * 2^52
+    const double z = kMagic - t;
+    const int m = __double2loint(z);                   // -round(t)
+    const double zr = z - kMagic;
+    const double d = t + zr;
+    double p = fma(d, 2.239395190875157e-12, -3.308302680541371e-09);
+    p = fma(p, d, 3.665565596910106e-06);
+    p = fma(p, d, -0.0027076061740622863);
+    p = fma(p, d, 1.0);
+    const double r = tab[m & (kExpTabSize - 1)] * p;
+    const double v = __hiloint2double(__double2hiint(r) + ((m >> kExpTabBits) << 20), __double2loint(r));
+    const unsigned ht = (unsigned)__double2hiint(t);   // t >= 258531 (s >= 700) or +inf -> 0, NaN propagates
+    return (ht - 0x410F8F17u <= 0x7FF00000u - 0x410F8F17u) ? 0.0 : v;
+}
 
 template <int KERN>
 __device__ __forceinline__ double kappa_of_r2(double r2, double power, const double* __restrict__ tab) {
-    if (KERN == 0) return exp_neg_fast(r2, tab);                 // RBF: exp(-r^2/2), r2 already halved
+    if (KERN == 0) return exp_neg_tab_units(r2, tab);            // RBF: r2 is already (r^2 / 2) * 256 / ln 2
     double r = sqrt(r2);
     if (KERN == 1) return exp_neg_fast(r, tab);                  // Exponential
     if (KERN == 2) {                                             // Matern32
@@ -110,7 +127,13 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
                                                             const RawOut* __restrict__ raws, int ldraw) {
     // single right-hand side + small column bucket (the first-order scoring path): staging is double buffered
     constexpr bool DB = ONE_RHS && MODE == 0 && NCB <= 11;
-    using SM = EvalSmem<NXB, NCB, CPT, RG, MODE, DB>;
+    // RBF: the squared distance is formed in EXPANDED form, t = |x|^2 + |X_i|^2 - 2 x.X_i (4 instead of 6 FP64
+    // instructions per pair; the absolute error u (|x|^2 + |X_i|^2) of t is a relative 1e-14 of exp(-t ln2/256), far
+    // inside the 1e-9 gate -- it is also the form GPy itself uses).  The record then carries -2 X_i and |X_i|^2
+    // (GpView::XsE, nx + 1 doubles per row) instead of X_i.
+    constexpr bool kExpanded = (KERN == 0);
+    constexpr int NXR = NXB + (kExpanded ? 1 : 0);               // x slots of a record
+    using SM = EvalSmem<NXR, NCB, CPT, RG, MODE, DB>;
     constexpr int RS = SM::RS;
     constexpr int kEvalRows = SM::kRows;
     constexpr int TPG = kBlk / CPT;                              // threads per row group (each covers the 128 candidates)
@@ -134,12 +157,13 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
     if (KERN <= 3)                                               // kernels evaluated with exp_neg_fast
         for (int k = tid; k < kExpTabSize; k += kEvalThreads) sTab[k] = kExp2Tab[k];
 
-    double xs[CPT][NXB];
+    double xs[CPT][NXB], cx[CPT];
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
         const int slot = slot0 + eval_col<CPT, TPG>(s, j);
         const bool valid = slot < count;
         const int cand = valid ? (g.idx ? g.idx[slot] : slot) : 0;
+        cx[j] = 0.0;
 #pragma unroll
         for (int d = 0; d < NXB; ++d) {
             double v = 0.0;
@@ -148,6 +172,7 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
                 v = (x - g.xmin[d]) * g.xscale[d];              // trans_x, then GPy's X / lengthscale, as one multiply
             }
             xs[j][d] = v;
+            cx[j] = fma(v, v, cx[j]);                            // |x|^2 of the expanded form
         }
     }
     double acc[CPT][NCB];
@@ -156,7 +181,8 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
 #pragma unroll
         for (int c = 0; c < NCB; ++c) acc[j][c] = 0.0;
 
-    const double* __restrict__ gX = g.Xs;
+    const double* __restrict__ gX = kExpanded ? g.XsE : g.Xs;
+    const int nxs = kExpanded ? nx + 1 : nx;                     // doubles per training row in gX
     const double* __restrict__ gC = (MODE == 0) ? g.C : g.H;
     const double* __restrict__ gG = g.G;
     double* __restrict__ pan = nullptr;
@@ -169,13 +195,15 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
     auto stage_async = [&](int i0, int buf) {
         double* dRec = smem + buf * SM::kStage;
         double* dG = dRec + SM::kRec;
-        for (int k = tid; k < kEvalRows * NXB; k += kEvalThreads) {
-            const int row = k / NXB, d = k % NXB;
-            if (d < nx) cp_async8(dRec + row * RS + d, gX + (size_t)(i0 + row) * nx + d);
+        for (int k = tid; k < kEvalRows * NXR; k += kEvalThreads) {
+            const int row = k / NXR, d = k % NXR;
+            // expanded form: source column nx (|X_i|^2) goes to the last x slot, the padding slots in between stay 0
+            if (d < nx) cp_async8(dRec + row * RS + d, gX + (size_t)(i0 + row) * nxs + d);
+            else if (kExpanded && d == NXB) cp_async8(dRec + row * RS + d, gX + (size_t)(i0 + row) * nxs + nx);
         }
         for (int k = tid; k < kEvalRows * NCB; k += kEvalThreads) {
             const int c = k / kEvalRows, row = k % kEvalRows;
-            if (c < ncols) cp_async8(dRec + row * RS + NXB + c, gC + (size_t)c * n_pad + i0 + row);
+            if (c < ncols) cp_async8(dRec + row * RS + NXR + c, gC + (size_t)c * n_pad + i0 + row);
         }
         for (int k = tid; k < kEvalRows; k += kEvalThreads) cp_async8(dG + k, gG + i0 + k);
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -195,13 +223,16 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
             sG = sRec + SM::kRec;
         } else {
         __syncthreads();
-        for (int k = tid; k < kEvalRows * NXB; k += kEvalThreads) {
-            const int row = k / NXB, d = k % NXB;
-            sRec[row * RS + d] = (d < nx) ? gX[(size_t)(i0 + row) * nx + d] : 0.0;
+        for (int k = tid; k < kEvalRows * NXR; k += kEvalThreads) {
+            const int row = k / NXR, d = k % NXR;
+            double v = 0.0;
+            if (d < nx) v = gX[(size_t)(i0 + row) * nxs + d];
+            else if (kExpanded && d == NXB) v = gX[(size_t)(i0 + row) * nxs + nx];
+            sRec[row * RS + d] = v;
         }
         for (int k = tid; k < kEvalRows * NCB; k += kEvalThreads) {
             const int c = k / kEvalRows, row = k % kEvalRows;
-            sRec[row * RS + NXB + c] = (c < ncols) ? gC[(size_t)c * n_pad + i0 + row] : 0.0;
+            sRec[row * RS + NXR + c] = (c < ncols) ? gC[(size_t)c * n_pad + i0 + row] : 0.0;
         }
         if (MODE == 0) {
             for (int k = tid; k < kEvalRows * nrhs; k += kEvalThreads) {
@@ -214,8 +245,8 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
 #pragma unroll kEvalUnroll
         for (int ii = rg; ii < kEvalRows; ii += RG) {
             const double* __restrict__ rec = sRec + ii * RS;
-            double xr[NXB], cr[NCB];
-            if (NXB % 2 == 0) {
+            double xr[NXR], cr[NCB];
+            if (NXR % 2 == 0 && !kExpanded) {
 #pragma unroll
                 for (int d = 0; d < NXB; d += 2) {
                     const double2 v = *reinterpret_cast<const double2*>(rec + d);
@@ -225,7 +256,7 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
 #pragma unroll
                 for (int c = 0; c < NCB; ++c) cr[c] = rec[NXB + c];
             } else {
-                // odd NXB: the record [x | C columns] is read as RS/2 16-byte vectors
+                // odd NXB / expanded form: the record [x | C columns] is read as RS/2 16-byte vectors
                 double rv[RS];
 #pragma unroll
                 for (int d = 0; d < RS; d += 2) {
@@ -234,20 +265,27 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 51
                     rv[d + 1] = v.y;
                 }
 #pragma unroll
-                for (int d = 0; d < NXB; ++d) xr[d] = rv[d];
+                for (int d = 0; d < NXR; ++d) xr[d] = rv[d];
 #pragma unroll
-                for (int c = 0; c < NCB; ++c) cr[c] = rv[NXB + c];
+                for (int c = 0; c < NCB; ++c) cr[c] = rv[NXR + c];
             }
             const int row = i0 + ii;
             const int sw = (row & 3) << 2;
             double kap[CPT];
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
-                double r2 = 0.0;
+                double r2;
+                if (kExpanded) {
+                    r2 = cx[j] + xr[NXB];                        // |x|^2 + |X_i|^2
 #pragma unroll
-                for (int d = 0; d < NXB; ++d) {
-                    const double df = xs[j][d] - xr[d];
-                    r2 = fma(df, df, r2);
+                    for (int d = 0; d < NXB; ++d) r2 = fma(xs[j][d], xr[d], r2);   // xr = -2 X_i
+                } else {
+                    r2 = 0.0;
+#pragma unroll
+                    for (int d = 0; d < NXB; ++d) {
+                        const double df = xs[j][d] - xr[d];
+                        r2 = fma(df, df, r2);
+                    }
                 }
                 kap[j] = kappa_of_r2<KERN>(r2, power, sTab);
             }

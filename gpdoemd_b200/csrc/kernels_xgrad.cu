@@ -19,7 +19,6 @@
 
 namespace gpd {
 
-constexpr double kRbfCoordScaleX = 0.70710678118654752440;   // == kRbfCoordScale of eval_impl.cuh (Xs is pre-scaled)
 
 // grid (tiles, nGP), 128 threads: thread t = candidate t of the tile.  acc_out: [gp][chunk_n][(1+nx)*(1+P)]
 __global__ void __launch_bounds__(kBlk) xgrad_eval_kernel(const GpView* __restrict__ gps, const double* __restrict__ X,
@@ -30,7 +29,7 @@ __global__ void __launch_bounds__(kBlk) xgrad_eval_kernel(const GpView* __restri
     const int cand = tile * kBlk + t;
     const bool valid = cand < chunk_n;
     const int nx = g.nx, P = g.P, n_pad = g.n_pad, nk = 1 + nx, ncol = 1 + P;
-    const double cs = (g.kernel == 0) ? kRbfCoordScaleX : 1.0;      // Xs and xscale carry sqrt(1/2) for the RBF kernel
+    const double cs = (g.kernel == 0) ? kRbfCoordScale : 1.0;      // Xs and xscale carry kRbfCoordScale for the RBF kernel
     double xs[kMaxXDims];
     for (int d = 0; d < nx; ++d)
         xs[d] = valid ? (X[(size_t)cand * ldx + g.x_active[d]] - g.xmin[d]) * g.xscale[d] / cs : 0.0;   // = trans_x(x)/l
