@@ -1932,14 +1932,16 @@ int gpd_marginal_dx(gpd_model* mo, const double* X, int64_t N, double* mu_out, d
     const int nx = g0->nx, NR = 1 + nx, ncol = 1 + P, NG = NR * (NR + 1) / 2;
     // scratch per candidate: X, 2 panel sets (in / out), contractions, Gram rows, outputs
     const size_t per = sizeof(double) * ((size_t)D + 2 * (size_t)n_pad_sum * NR + (size_t)G * (NR * ncol + NG) +
-                                         (size_t)E * (1 + E) * (1 + D));
-    GPD_CHECK(c->scratch_limit > (size_t)kBlk * per + (8u << 20), "scratch limit too small for the design-gradient path");
-    int64_t chunk = (int64_t)((c->scratch_limit - (8u << 20)) / per) / kBlk * kBlk;
+                                         (size_t)E * (1 + E) * (1 + D)) +
+                       ((size_t)G * sizeof(Item) + kBlk - 1) / kBlk;            // one work item per (GP, tile)
+    GPD_CHECK(c->scratch_limit > (size_t)kBlk * per + (8u << 20) + (size_t)G * sizeof(GpView),
+              "scratch limit too small for the design-gradient path");
+    int64_t chunk = (int64_t)((c->scratch_limit - (8u << 20) - (size_t)G * sizeof(GpView)) / per) / kBlk * kBlk;
     chunk = std::min<int64_t>(chunk, 1 << 20);
     chunk = std::min<int64_t>(chunk, (N + kBlk - 1) / kBlk * kBlk);
     GPD_CHECK(chunk >= kBlk, "scratch limit too small");
     const int Nc = (int)chunk, tiles = Nc / kBlk;
-    GPD_TRY(ensure_scratch(c, per * (size_t)Nc + (8u << 20)));
+    GPD_TRY(ensure_scratch(c, per * (size_t)Nc + (8u << 20) + (size_t)G * sizeof(GpView)));
     Bump bump(c->scratch.p, c->scratch.cap);
     double* X_dev = bump.take<double>((size_t)Nc * D);
     double* pan_in = bump.take<double>((size_t)n_pad_sum * NR * Nc);
