@@ -97,6 +97,7 @@ _SIGNATURES = {
     'gpd_host_free_pinned': (C.c_int, [C.c_void_p, C.c_void_p]),
     'gpd_dev_fill_uniform': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_int64,
                                        c_double_p, c_double_p]),
+    'gpd_debug_check_scratch': (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     'gpd_layout_a_index': (C.c_int32, [C.c_int32] * 3),
     'gpd_layout_a_row': (C.c_int32, [C.c_int32] * 2),
     'gpd_layout_a_col': (C.c_int32, [C.c_int32] * 2),

@@ -30,6 +30,12 @@ class Context:
     def set_option(self, name, value):
         check(self.lib.gpd_set_option(self.handle, name.encode(), int(value)))
 
+    def check_scratch(self):
+        """(number of red zones, overwritten bytes) of the current scratch layout; needs set_option('scratch_redzones', 1)."""
+        z, b = C.c_int64(), C.c_int64()
+        check(self.lib.gpd_debug_check_scratch(self.handle, C.byref(z), C.byref(b)))
+        return int(z.value), int(b.value)
+
     def launch_count(self):
         return int(self.lib.gpd_launch_count(self.handle))
 

@@ -55,6 +55,8 @@ struct gpd_ctx {
     cudaStream_t stream2 = nullptr;         // low priority: only the evaluation overlapped with a tail wave (run_chunk)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int tail_overlap = 1;                   // option "tail_overlap"
+    int redzones = 0, redzone_selftest = 0; // option "scratch_redzones" (debug)
+    std::vector<size_t> zones;              // offsets of the red zones of the current scratch layout
     int head_periods = 0, head_grid = 0;    // options "head_periods" / "head_grid": see plan_materialize (tail overlap)
     int tri_parts_auto = 0, tri_parts = 0;  // option "tri_parts": 0 (default) / -1 = whole items, 9 = by factor size, 1..8 forced
     int fused = 0;                          // option "fused": first-order path through the fused evaluation + contraction kernel
@@ -168,15 +170,29 @@ static int resolve_spans(gpd_ctx* c) {
 }
 
 // bump allocator over the context scratch region
+// Option "scratch_redzones" (debug; compute-sanitizer is not available on this pool): every sub-buffer carved out of
+// the scratch region is followed by a 256-byte red zone filled with 0xCB in stream order before the call's kernels run;
+// gpd_debug_check_scratch counts the bytes that no longer hold the pattern.  The scratch region is where every
+// N-sized write of the library lands (panels, raw contractions, hook outputs, criterion workspace, work-item lists).
+constexpr size_t kRedZone = 256;
 struct Bump {
     char* base;
     size_t off = 0, cap;
-    Bump(void* p, size_t c) : base((char*)p), cap(c) {}
+    gpd_ctx* ctx;
+    Bump(void* p, size_t c, gpd_ctx* owner = nullptr) : base((char*)p), cap(c), ctx(owner) {}
     template <typename T>
     T* take(size_t count) {
         off = align_up(off, 256);
         T* r = (T*)(base + off);
         off += count * sizeof(T);
+        if (ctx && ctx->redzones) {
+            off = align_up(off, 256);
+            if (off + kRedZone <= cap) {
+                cudaMemsetAsync(base + off, 0xCB, kRedZone, ctx->stream);
+                ctx->zones.push_back(off);
+            }
+            off += kRedZone;
+        }
         return r;
     }
 };
@@ -776,7 +792,8 @@ static int run_chunk(gpd_ctx* c, Plan& pl, double* X_dev, int ldx, int nc, const
 static int ensure_scratch(gpd_ctx* c, size_t bytes) {
     GPD_CHECK(bytes <= c->scratch_limit + (64u << 20), "internal: plan exceeds the scratch limit");
     c->epoch++;                       // the caller is about to overwrite the scratch region
-    return c->scratch.ensure(bytes);
+    c->zones.clear();
+    return c->scratch.ensure(bytes + (c->redzones ? (1u << 20) : 0));
 }
 
 static int upload_model_state(gpd_model* mo);
@@ -887,6 +904,16 @@ int gpd_set_option(gpd_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "tail_overlap")) {
         GPD_CHECK(value == 0 || value == 1, "tail_overlap is 0 or 1");
         c->tail_overlap = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "scratch_redzones")) {
+        GPD_CHECK(value >= 0 && value <= 2, "scratch_redzones is 0, 1, or 2 (self-test: the next check first damages one byte)");
+        if (value == 2) {
+            c->redzone_selftest = 1;
+            return 0;
+        }
+        c->redzones = (int)value;
+        c->zones.clear();
         return 0;
     }
     if (!strcmp(name, "head_periods")) {
@@ -1481,7 +1508,7 @@ static int hooks_host(gpd_model* mo, const double* X, int64_t N, int flags, cons
     const size_t total = pl.per_cand_bytes * ((size_t)pl.chunk + kBlk) + (8u << 20) + pl.fixed_bytes + pl.entries.size() * sizeof(GpView) +
                          (size_t)pl.entries.size() * pl.tiles * sizeof(Item) * 10;
     GPD_TRY(ensure_scratch(c, total));
-    Bump bump(c->scratch.p, c->scratch.cap);
+    Bump bump(c->scratch.p, c->scratch.cap, c);
     double* X_dev = bump.take<double>((size_t)pl.chunk * D);
     GPD_TRY(plan_materialize(c, pl, bump));
     cudaStream_t s = c->stream;
@@ -1570,7 +1597,7 @@ int gpd_marginal(gpd_model* mo, const double* X, int64_t N, int order, double* m
     const size_t total = pl.per_cand_bytes * ((size_t)pl.chunk + kBlk) + (8u << 20) + pl.fixed_bytes + pl.entries.size() * sizeof(GpView) +
                          (size_t)pl.entries.size() * pl.tiles * sizeof(Item) * 10;
     GPD_TRY(ensure_scratch(c, total));
-    Bump bump(c->scratch.p, c->scratch.cap);
+    Bump bump(c->scratch.p, c->scratch.cap, c);
     double* X_dev = bump.take<double>((size_t)pl.chunk * D);
     double* S_dev = bump.take<double>((size_t)pl.chunk * E * E);
     double* tmpA = order == 2 ? bump.take<double>((size_t)pl.chunk * E * P * P) : nullptr;
@@ -1609,7 +1636,7 @@ int gpd_marginal_assemble(gpd_ctx* c, int order, int64_t N, int32_t E, int32_t P
     int64_t chunk = std::min<int64_t>(N, std::max<int64_t>(1, (int64_t)((c->scratch_limit - (1 << 20)) / per)));
     chunk = std::min<int64_t>(chunk, 1 << 24);
     GPD_TRY(ensure_scratch(c, per * (size_t)chunk + (1 << 20)));
-    Bump bump(c->scratch.p, c->scratch.cap);
+    Bump bump(c->scratch.p, c->scratch.cap, c);
     double* d_mu = bump.take<double>((size_t)chunk * E);
     double* d_s2 = bump.take<double>((size_t)chunk * E);
     double* d_dmu = bump.take<double>((size_t)chunk * E * P);
@@ -1660,7 +1687,7 @@ int gpd_criterion(gpd_ctx* c, int kind, const double* mu, const double* S, int64
     int64_t chunk = std::min<int64_t>(N, std::max<int64_t>(1, (int64_t)((c->scratch_limit - (1 << 20)) / per)));
     chunk = std::min<int64_t>(chunk, 1 << 24);
     GPD_TRY(ensure_scratch(c, per * (size_t)chunk + (1 << 20)));
-    Bump bump(c->scratch.p, c->scratch.cap);
+    Bump bump(c->scratch.p, c->scratch.cap, c);
     double* d_mu = bump.take<double>((size_t)chunk * M * E);
     double* d_S = bump.take<double>((size_t)chunk * M * E * E);
     double* d_dc = bump.take<double>((size_t)chunk);
@@ -1698,7 +1725,7 @@ int gpd_gauss_loglik(gpd_ctx* c, const double* Y, const double* M, const double*
     const size_t per = sizeof(double) * ((size_t)E + (size_t)N * (E + (size_t)E * E + 2));
     int64_t chunk = std::min<int64_t>(n, std::max<int64_t>(1, (int64_t)((c->scratch_limit - (1 << 20)) / per)));
     GPD_TRY(ensure_scratch(c, per * (size_t)chunk + (1 << 20)));
-    Bump bump(c->scratch.p, c->scratch.cap);
+    Bump bump(c->scratch.p, c->scratch.cap, c);
     double* d_Y = bump.take<double>((size_t)chunk * E);
     double* d_M = bump.take<double>((size_t)chunk * N * E);
     double* d_S = bump.take<double>((size_t)chunk * N * E * E);
@@ -1791,7 +1818,7 @@ static int score_impl(gpd_ctx* c, gpd_model* const* models, int32_t M, const dou
         const size_t total = pl.per_cand_bytes * ((size_t)pl.chunk + kBlk) + (8u << 20) + pl.fixed_bytes + pl.entries.size() * sizeof(GpView) +
                              (size_t)pl.entries.size() * pl.tiles * sizeof(Item) * 10;
         GPD_TRY(ensure_scratch(c, total));
-        Bump bump(c->scratch.p, c->scratch.cap);
+        Bump bump(c->scratch.p, c->scratch.cap, c);
         const int Nc0 = pl.chunk;
         st->X_stage = x_on_device ? nullptr : bump.take<double>((size_t)Nc0 * D);
         st->mu_all = order == 2 ? bump.take<double>((size_t)Nc0 * M * E) : nullptr;
@@ -1942,7 +1969,7 @@ int gpd_marginal_dx(gpd_model* mo, const double* X, int64_t N, double* mu_out, d
     GPD_CHECK(chunk >= kBlk, "scratch limit too small");
     const int Nc = (int)chunk, tiles = Nc / kBlk;
     GPD_TRY(ensure_scratch(c, per * (size_t)Nc + (8u << 20) + (size_t)G * sizeof(GpView)));
-    Bump bump(c->scratch.p, c->scratch.cap);
+    Bump bump(c->scratch.p, c->scratch.cap, c);
     double* X_dev = bump.take<double>((size_t)Nc * D);
     double* pan_in = bump.take<double>((size_t)n_pad_sum * NR * Nc);
     double* pan_out = bump.take<double>((size_t)n_pad_sum * NR * Nc);
@@ -2142,7 +2169,7 @@ int gpd_marginals(gpd_ctx* c, gpd_model* const* models, int32_t M, const double*
         gpd_resident_free(res);
         return rc;
     }
-    Bump bump(c->scratch.p, c->scratch.cap);
+    Bump bump(c->scratch.p, c->scratch.cap, c);
     const int Nc = pl.chunk;
     double* X_dev = bump.take<double>((size_t)Nc * D);
     double* mu_tmp = res ? nullptr : bump.take<double>((size_t)Nc * M * E);
@@ -2208,7 +2235,7 @@ int gpd_criterion_resident(gpd_ctx* c, int kind, const gpd_resident* r, const do
     int64_t chunk = std::min<int64_t>(N, std::max<int64_t>(1, (int64_t)((c->scratch_limit - (1 << 20)) / per)));
     chunk = std::min<int64_t>(chunk, 1 << 24);
     GPD_TRY(ensure_scratch(c, per * (size_t)chunk + (1 << 20)));
-    Bump bump(c->scratch.p, c->scratch.cap);
+    Bump bump(c->scratch.p, c->scratch.cap, c);
     double* d_dc = bump.take<double>((size_t)chunk);
     double* d_work = bump.take<double>(criterion_work_doubles((int)chunk, M, E));
     double* d_noise = bump.take<double>((size_t)E * E);
@@ -2426,6 +2453,27 @@ int gpd_score_sharded(gpd_ctx* c, gpd_comm* cm, gpd_model* const* models, int32_
         if (best_val) best_val[k] = bv[k];
         if (best_idx) best_idx[k] = bi[k];
     }
+    return 0;
+}
+
+/* debug: bytes of the scratch red zones (option "scratch_redzones") that were overwritten since the last planning */
+int gpd_debug_check_scratch(gpd_ctx* c, int64_t* zones_out, int64_t* bad_bytes_out) {
+    GPD_CHECK(c && zones_out && bad_bytes_out, "null argument");
+    GPD_CUDA(cudaSetDevice(c->device));
+    GPD_CUDA(cudaStreamSynchronize(c->stream));
+    int64_t bad = 0;
+    unsigned char host[kRedZone];
+    if (c->redzone_selftest && !c->zones.empty()) {      // the detector must see a single damaged byte
+        GPD_CUDA(cudaMemset((char*)c->scratch.p + c->zones.back() + 17, 0x00, 1));
+        c->redzone_selftest = 0;
+    }
+    for (size_t off : c->zones) {
+        if (off + kRedZone > c->scratch.cap) continue;
+        GPD_CUDA(cudaMemcpy(host, (const char*)c->scratch.p + off, kRedZone, cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < kRedZone; ++k) bad += host[k] != 0xCB;
+    }
+    *zones_out = (int64_t)c->zones.size();
+    *bad_bytes_out = bad;
     return 0;
 }
 

@@ -96,6 +96,7 @@ int  gpd_set_scratch_bytes(gpd_ctx* ctx, uint64_t bytes);
  * "fused" 0 (default) / 1 = first-order path through ONE persistent kernel that evaluates the kernel rows into a private
  *   L2-resident panel and contracts them in place: O(SMs * n) scratch instead of O(N * n), measured 1-8 % slower than the
  *   separate kernels;
+ * "scratch_redzones" 0 (default) / 1 = debug red zones behind every scratch sub-buffer, see gpd_debug_check_scratch;
  * "head_periods" 0 (default) .. 16 / "head_grid" 0 (all SMs) or a CTA count: a longer tail-overlap head on a restricted
  *   grid (measured neutral on C2);
  * "tri_parts" 0 (default) = whole work items, 1..8 = every (GP, tile) item of the first-order contraction cut into that
@@ -270,6 +271,12 @@ int  gpd_host_free_pinned(gpd_ctx* ctx, void* host);
  * global stream starts at counter (first_row + i); shards reproduce the same rows */
 int  gpd_dev_fill_uniform(gpd_ctx* ctx, double* X_dev, int64_t N, int32_t D, uint64_t seed,
                           int64_t first_row, const double* lo, const double* hi);
+
+/* ---- debug: a memcheck of our own for the scratch region (compute-sanitizer is not available on the target pool) ----
+ * with gpd_set_option(ctx, "scratch_redzones", 1) every sub-buffer of the per-call scratch region is followed by a
+ * 256-byte red zone; this call reports how many zones the current layout has and how many of their bytes were
+ * overwritten (must be 0).  tests/test_scratch_redzones.py runs the ragged-size matrix with it. */
+int  gpd_debug_check_scratch(gpd_ctx* ctx, int64_t* zones_out, int64_t* bad_bytes_out);
 
 /* ---- layout self-description (used by the CPU tests to check the DMMA operand packing) ---- */
 int32_t gpd_layout_a_index(int32_t ms, int32_t ks, int32_t lane);
