@@ -60,6 +60,7 @@ struct gpd_ctx {
     int head_periods = 0, head_grid = 0;    // options "head_periods" / "head_grid": see plan_materialize (tail overlap)
     int tri_parts_auto = 0, tri_parts = 0;  // option "tri_parts": 0 (default) / -1 = whole items, 9 = by factor size, 1..8 forced
     int fused = 0;                          // option "fused": first-order path through the fused evaluation + contraction kernel
+    int setup_variant = 1;                  // option "setup_variant": 1 = per-GP setup on the tensor pipe (kernels_inv.cu), 0 = round-1 FMA kernels
     uint64_t scratch_limit = 6ull << 30;
     DevBuf scratch, tables, flush;
     uint64_t launches = 0;
@@ -937,6 +938,11 @@ int gpd_set_option(gpd_ctx* c, const char* name, int64_t value) {
         c->fused = (int)value;
         return 0;
     }
+    if (!strcmp(name, "setup_variant")) {
+        GPD_CHECK(value == 0 || value == 1, "setup_variant is 0 (FP64 FMA setup kernels) or 1 (tensor-pipe setup kernels)");
+        c->setup_variant = (int)value;
+        return 0;
+    }
     if (!strcmp(name, "tri_trim")) {
         GPD_CHECK(value == 0 || value == 1, "tri_trim is 0 or 1");
         c->tri_trim = (int)value;
@@ -1215,7 +1221,8 @@ static int gp_pack_factor(gpd_ctx* c, gpd_gp* g, const double* L_dev, int factor
         return 1;
     }
     uint64_t nl = 0;
-    int rc = launch_invert_and_pack(c->stream, L_dev, g->n, g->n_pad, dense, g->LinvF, g->LinvB, &nl, factor_kind);
+    int rc = launch_invert_and_pack(c->stream, L_dev, g->n, g->n_pad, dense, g->LinvF, g->LinvB, &nl, factor_kind,
+                                    c->setup_variant);
     c->launches += nl;
     if (c->profile) c->fam_launches[F_SETUP] += nl;
     cudaError_t e = cudaStreamSynchronize(c->stream);
@@ -1308,7 +1315,7 @@ int gpd_gp_build(gpd_ctx* c, const gpd_gp_desc* d, const double* Y, double noise
             if (e != cudaSuccess) break;
             uint64_t nl = 1;
             rc = launch_kmat(s, ka, Z_dev, A);
-            if (!rc) rc = launch_cholesky(s, A, n, info_dev, &nl);
+            if (!rc) rc = launch_cholesky(s, A, n, info_dev, &nl, c->setup_variant);
             c->launches += nl;
             if (c->profile) c->fam_launches[F_SETUP] += nl;
             if (rc) break;
@@ -1324,8 +1331,10 @@ int gpd_gp_build(gpd_ctx* c, const gpd_gp_desc* d, const double* Y, double noise
         }
     }
     if (e == cudaSuccess && !rc) {
-        rc = launch_chol_solve(s, A, n, y_dev, g->alpha);
-        c->launches += 1;
+        uint64_t nls = 0;
+        rc = launch_chol_solve(s, A, n, y_dev, g->alpha, &nls, c->setup_variant);
+        c->launches += nls;
+        if (c->profile) c->fam_launches[F_SETUP] += nls;
         if (!rc && alpha_out) e = cudaMemcpyAsync(alpha_out, g->alpha, sizeof(double) * n, cudaMemcpyDeviceToHost, s);
         if (!rc && e == cudaSuccess && L_out)
             e = cudaMemcpyAsync(L_out, A, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, s);

@@ -158,7 +158,9 @@ int launch_beta_contract(cudaStream_t s, const GpView* gps_dev, const Item* item
                          const double* beta_panels, const RawOut* raw_dev);
 // kernels_tri.cu
 int launch_invert_and_pack(cudaStream_t s, const double* L_dev, int n, int n_pad, double* dense_tmp,
-                           double* packF, double* packB, uint64_t* launches, int factor_kind);
+                           double* packF, double* packB, uint64_t* launches, int factor_kind, int setup_variant);
+// kernels_inv.cu
+int launch_invert_offdiag_dmma(cudaStream_t s, const double* L_dev, int n, int n_pad, double* X, uint64_t* launches);
 int launch_tri(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, int nitems, int nwork_rhs,
                int in_stride, int out_stride, int backward, const double* panels_in, double* panels_out,
                const RawOut* raw_dev, int ng, int chunk_n, int num_sms, int variant, int cps, int trim);
@@ -173,8 +175,9 @@ int launch_xgrad_eval(cudaStream_t s, const GpView* gps_dev, int ngp, int tiles,
 int launch_xgrad_finalize(cudaStream_t s, const XgradArgs& a);
 // kernels_build.cu
 int launch_kmat(cudaStream_t s, const KmatArgs& a, const double* Z_dev, double* A_dev);
-int launch_cholesky(cudaStream_t s, double* A_dev, int n, int* info_dev, uint64_t* launches);
-int launch_chol_solve(cudaStream_t s, const double* L_dev, int n, const double* y_dev, double* x_dev);
+int launch_cholesky(cudaStream_t s, double* A_dev, int n, int* info_dev, uint64_t* launches, int setup_variant);
+int launch_chol_solve(cudaStream_t s, const double* L_dev, int n, const double* y_dev, double* x_dev, uint64_t* launches,
+                      int setup_variant);
 // kernels_crit.cu
 int launch_route(cudaStream_t s, const double* X_dev, int ldx, int chunk_n, int nb, const int* bcols,
                  const int* weights, int ncombo, int* idx, int* counts, int idx_stride);

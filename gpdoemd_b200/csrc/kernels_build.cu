@@ -270,6 +270,176 @@ __global__ void __launch_bounds__(1024) chol_solve_kernel(const double* __restri
     }
 }
 
+// =============================================================================================
+// Round-2 setup kernels (option "setup_variant" = 1, the default).  Same algorithms and the same substitutions as
+// above (blocked right-looking Cholesky, dpotrs-style solves), re-organised so that a thread owns a ROW and keeps a
+// 16-column slice of it in registers: no integer divisions in inner loops, two barriers per column in the diagonal
+// block and none at all in the panel; alpha's two substitutions run over many CTAs instead of one.
+// =============================================================================================
+constexpr int kSlice = 16;                  // columns of a row held in registers
+
+// A_JJ = L_JJ L_JJ^T in shared memory, one thread per row.  Left-looking over 16-column slices:
+//   p[j] = A[i][c0+j] - sum_{m<c0} L[i][m] L[c0+j][m]      (registers, L[c0+j][m] is a broadcast load)
+// then the 16 columns of the slice are finished right-looking inside the slice.
+__global__ void __launch_bounds__(kBlk) chol_diag_rows_kernel(double* __restrict__ A, int n, int J, int* __restrict__ info) {
+    extern __shared__ double S[];   // [128][kCholLd]
+    const int r0 = J * kBlk, bs = min(kBlk, n - r0);
+    const int i = threadIdx.x;
+    // rows/columns >= bs are identity padding, so the loops below have compile-time bounds
+    for (int r = 0; r < kBlk; ++r) {
+        double v = (r == i) ? 1.0 : 0.0;
+        if (r < bs && i < bs) v = (i <= r) ? A[(size_t)(r0 + r) * n + r0 + i] : 0.0;   // coalesced rows of the lower triangle
+        S[r * kCholLd + i] = v;
+    }
+    __syncthreads();
+    double* __restrict__ rowi = S + i * kCholLd;
+    for (int c0 = 0; c0 < kBlk; c0 += kSlice) {
+        double p[kSlice];
+#pragma unroll
+        for (int j = 0; j < kSlice; ++j) p[j] = rowi[c0 + j];
+        if (i >= c0) {
+            for (int m = 0; m < c0; ++m) {
+                const double li = rowi[m];
+#pragma unroll
+                for (int j = 0; j < kSlice; ++j) p[j] = fma(-li, S[(c0 + j) * kCholLd + m], p[j]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kSlice; ++k) {
+            const int g = c0 + k;
+            if (i == g) {
+                double d = p[k];
+                if (!(d > 0.0)) {           // not positive definite (also catches NaN): GPy jitchol retries with jitter
+                    atomicMin(info, r0 + g + 1);
+                    d = 1.0;
+                }
+                rowi[g] = sqrt(d);
+            }
+            __syncthreads();
+            if (i > g) {
+                p[k] = p[k] / S[g * kCholLd + g];
+                rowi[g] = p[k];
+            }
+            __syncthreads();
+            if (i > g) {
+#pragma unroll
+                for (int j = k + 1; j < kSlice; ++j) p[j] = fma(-p[k], S[(c0 + j) * kCholLd + g], p[j]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int r = 0; r < bs; ++r)
+        if (i <= r) A[(size_t)(r0 + r) * n + r0 + i] = S[r * kCholLd + i];
+}
+
+// panel rows below the diagonal block:  X L_JJ^T = A_IJ, one thread per row, 32 rows per CTA, no barriers in the
+// substitution.  Finished columns of a row live in shared memory (column-major, conflict-free), the current 16 in
+// registers.
+constexpr int kPanelRows2 = 32;
+constexpr int kPanelLd2 = kPanelRows2 + 1;
+
+__global__ void __launch_bounds__(kPanelRows2) chol_panel_rows_kernel(double* __restrict__ A, int n, int J) {
+    extern __shared__ double sm[];
+    double* Ls = sm;                          // [128][kCholLd] L_JJ (lower), row c = coefficients of column c of X
+    double* Xs = sm + kBlk * kCholLd;         // [128][kPanelLd2] finished columns of this CTA's rows
+    const int c0g = J * kBlk;
+    const int row0 = (J + 1) * kBlk + blockIdx.x * kPanelRows2;
+    const int nrows = min(kPanelRows2, n - row0);
+    const int t = threadIdx.x;
+    for (int r = 0; r < kBlk; ++r)
+        for (int cc = t; cc < kBlk; cc += kPanelRows2) Ls[r * kCholLd + cc] = (cc <= r) ? A[(size_t)(c0g + r) * n + c0g + cc] : 0.0;
+    __syncthreads();
+    if (t < nrows) {
+        const double* __restrict__ arow = A + (size_t)(row0 + t) * n + c0g;
+        for (int c0 = 0; c0 < kBlk; c0 += kSlice) {
+            double p[kSlice];
+#pragma unroll
+            for (int j = 0; j < kSlice; ++j) p[j] = arow[c0 + j];
+            for (int m = 0; m < c0; ++m) {
+                const double xm = Xs[m * kPanelLd2 + t];
+#pragma unroll
+                for (int j = 0; j < kSlice; ++j) p[j] = fma(-xm, Ls[(c0 + j) * kCholLd + m], p[j]);
+            }
+#pragma unroll
+            for (int k = 0; k < kSlice; ++k) {
+                const int g = c0 + k;
+                p[k] = p[k] / Ls[g * kCholLd + g];
+                Xs[g * kPanelLd2 + t] = p[k];
+#pragma unroll
+                for (int j = k + 1; j < kSlice; ++j) p[j] = fma(-p[k], Ls[(c0 + j) * kCholLd + g], p[j]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int r = 0; r < nrows; ++r)                               // coalesced row stores
+        for (int cc = t; cc < kBlk; cc += kPanelRows2) A[(size_t)(row0 + r) * n + c0g + cc] = Xs[cc * kPanelLd2 + r];
+}
+
+// ---- alpha = L^-T (L^-1 y) as blocked substitution over many CTAs: per diagonal block one small solve kernel and
+// one update kernel for the rest of the vector (dpotrs order of operations inside a block) ----
+__global__ void __launch_bounds__(kBlk) solve_diag_kernel(const double* __restrict__ L, int n, int J, int transposed,
+                                                          double* __restrict__ x) {
+    extern __shared__ double S[];   // [128][kCholLd]
+    __shared__ double xb[kBlk];
+    const int r0 = J * kBlk, bs = min(kBlk, n - r0);
+    const int i = threadIdx.x;
+    for (int r = 0; r < bs; ++r)
+        if (i < bs) S[r * kCholLd + i] = (i <= r) ? L[(size_t)(r0 + r) * n + r0 + i] : 0.0;
+    if (i < bs) xb[i] = x[r0 + i];
+    __syncthreads();
+    if (!transposed) {
+        for (int c = 0; c < bs; ++c) {
+            if (i == c) xb[c] /= S[c * kCholLd + c];
+            __syncthreads();
+            if (i > c && i < bs) xb[i] = fma(-S[i * kCholLd + c], xb[c], xb[i]);
+            __syncthreads();
+        }
+    } else {
+        for (int c = bs - 1; c >= 0; --c) {
+            if (i == c) xb[c] /= S[c * kCholLd + c];
+            __syncthreads();
+            if (i < c) xb[i] = fma(-S[c * kCholLd + i], xb[c], xb[i]);   // (L^T)[i][c] = L[c][i]
+            __syncthreads();
+        }
+    }
+    if (i < bs) x[r0 + i] = xb[i];
+}
+
+// forward: x_i -= L[i][r0 .. r0+bs) . x_J for the rows below block J; one warp per row, lanes across the columns
+__global__ void __launch_bounds__(256) solve_update_fwd_kernel(const double* __restrict__ L, int n, int J, double* __restrict__ x) {
+    __shared__ double xb[kBlk];
+    const int r0 = J * kBlk, bs = min(kBlk, n - r0);
+    if (threadIdx.x < kBlk) xb[threadIdx.x] = threadIdx.x < bs ? x[r0 + threadIdx.x] : 0.0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = r0 + bs + blockIdx.x * 8 + warp;
+    if (i >= n) return;
+    const double* __restrict__ lrow = L + (size_t)i * n + r0;
+    double s = 0.0;
+    for (int c = lane; c < bs; c += 32) s = fma(lrow[c], xb[c], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) x[i] -= s;
+}
+
+// backward: x_i -= sum_c L[r0 + c][i] x_J[c] for the entries left of block J; one thread per i (coalesced rows of L)
+__global__ void __launch_bounds__(256) solve_update_bwd_kernel(const double* __restrict__ L, int n, int J, double* __restrict__ x) {
+    __shared__ double xb[kBlk];
+    const int r0 = J * kBlk, bs = min(kBlk, n - r0);
+    if (threadIdx.x < kBlk) xb[threadIdx.x] = threadIdx.x < bs ? x[r0 + threadIdx.x] : 0.0;
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r0) return;
+    double s0 = 0.0, s1 = 0.0;
+    int c = 0;
+    for (; c + 2 <= bs; c += 2) {
+        s0 = fma(L[(size_t)(r0 + c) * n + i], xb[c], s0);
+        s1 = fma(L[(size_t)(r0 + c + 1) * n + i], xb[c + 1], s1);
+    }
+    if (c < bs) s0 = fma(L[(size_t)(r0 + c) * n + i], xb[c], s0);
+    x[i] -= s0 + s1;
+}
+
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
@@ -282,26 +452,33 @@ int launch_kmat(cudaStream_t s, const KmatArgs& a, const double* Z_dev, double* 
 
 // in-place lower Cholesky of the n x n row-major matrix A (lower triangle read and written); *info_dev = n + 1 on
 // entry (by the caller), 1 + index of the first non-positive pivot on failure
-int launch_cholesky(cudaStream_t s, double* A_dev, int n, int* info_dev, uint64_t* launches) {
+int launch_cholesky(cudaStream_t s, double* A_dev, int n, int* info_dev, uint64_t* launches, int setup_variant) {
     static bool attr_done_dev[64] = {};          // function attributes are per device
     int attr_dev = 0;
     GPD_CUDA(cudaGetDevice(&attr_dev));
     bool& attr_done = attr_done_dev[attr_dev & 63];
     const int diag_smem = kBlk * kCholLd * (int)sizeof(double);
     const int panel_smem = (kBlk * kBlk + kBlk * kPanelLd) * (int)sizeof(double);
+    const int panel_smem2 = (kBlk * kCholLd + kBlk * kPanelLd2) * (int)sizeof(double);
     if (!attr_done) {
         GPD_CUDA(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
         GPD_CUDA(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, panel_smem));
+        GPD_CUDA(cudaFuncSetAttribute(chol_diag_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
+        GPD_CUDA(cudaFuncSetAttribute(chol_panel_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, panel_smem2));
         attr_done = true;
     }
     const int nblk = (n + kBlk - 1) / kBlk;
     for (int J = 0; J < nblk; ++J) {
-        chol_diag_kernel<<<1, 256, diag_smem, s>>>(A_dev, n, J, info_dev);
+        if (setup_variant >= 1) chol_diag_rows_kernel<<<1, kBlk, diag_smem, s>>>(A_dev, n, J, info_dev);
+        else chol_diag_kernel<<<1, 256, diag_smem, s>>>(A_dev, n, J, info_dev);
         GPD_CUDA(cudaGetLastError());
         *launches += 1;
         const int below = n - (J + 1) * kBlk;
         if (below <= 0) break;
-        chol_panel_kernel<<<(below + kPanelRows - 1) / kPanelRows, kPanelRows, panel_smem, s>>>(A_dev, n, J);
+        if (setup_variant >= 1)
+            chol_panel_rows_kernel<<<(below + kPanelRows2 - 1) / kPanelRows2, kPanelRows2, panel_smem2, s>>>(A_dev, n, J);
+        else
+            chol_panel_kernel<<<(below + kPanelRows - 1) / kPanelRows, kPanelRows, panel_smem, s>>>(A_dev, n, J);
         GPD_CUDA(cudaGetLastError());
         const int t = (below + kUpd - 1) / kUpd;
         chol_update_kernel<<<dim3(t, t), 256, 0, s>>>(A_dev, n, J);
@@ -311,16 +488,46 @@ int launch_cholesky(cudaStream_t s, double* A_dev, int n, int* info_dev, uint64_
     return 0;
 }
 
-int launch_chol_solve(cudaStream_t s, const double* L_dev, int n, const double* y_dev, double* x_dev) {
+int launch_chol_solve(cudaStream_t s, const double* L_dev, int n, const double* y_dev, double* x_dev, uint64_t* launches,
+                      int setup_variant) {
     static bool attr_done_dev[64] = {};          // function attributes are per device
     int attr_dev = 0;
     GPD_CUDA(cudaGetDevice(&attr_dev));
     bool& attr_done = attr_done_dev[attr_dev & 63];
     const int smem = (kBlk * kCholLd + kBlk) * (int)sizeof(double);
+    const int diag_smem = kBlk * kCholLd * (int)sizeof(double);
     if (!attr_done) {
         GPD_CUDA(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        GPD_CUDA(cudaFuncSetAttribute(solve_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
         attr_done = true;
     }
+    if (setup_variant >= 1) {
+        const int nblk = (n + kBlk - 1) / kBlk;
+        GPD_CUDA(cudaMemcpyAsync(x_dev, y_dev, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+        for (int J = 0; J < nblk; ++J) {                       // L t = y
+            solve_diag_kernel<<<1, kBlk, diag_smem, s>>>(L_dev, n, J, 0, x_dev);
+            GPD_CUDA(cudaGetLastError());
+            *launches += 1;
+            const int below = n - (J + 1) * kBlk;
+            if (below > 0) {
+                solve_update_fwd_kernel<<<(below + 7) / 8, 256, 0, s>>>(L_dev, n, J, x_dev);
+                GPD_CUDA(cudaGetLastError());
+                *launches += 1;
+            }
+        }
+        for (int J = nblk - 1; J >= 0; --J) {                  // L^T alpha = t
+            solve_diag_kernel<<<1, kBlk, diag_smem, s>>>(L_dev, n, J, 1, x_dev);
+            GPD_CUDA(cudaGetLastError());
+            *launches += 1;
+            if (J > 0) {
+                solve_update_bwd_kernel<<<(J * kBlk + 255) / 256, 256, 0, s>>>(L_dev, n, J, x_dev);
+                GPD_CUDA(cudaGetLastError());
+                *launches += 1;
+            }
+        }
+        return 0;
+    }
+    *launches += 1;
     chol_solve_kernel<<<1, 1024, smem, s>>>(L_dev, n, y_dev, x_dev);
     GPD_CUDA(cudaGetLastError());
     return 0;

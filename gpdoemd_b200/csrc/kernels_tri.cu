@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(256) copy_lower_kernel(const double* __restric
 }
 
 int launch_invert_and_pack(cudaStream_t s, const double* L_dev, int n, int n_pad, double* dense_tmp, double* packF,
-                           double* packB, uint64_t* launches, int factor_kind) {
+                           double* packB, uint64_t* launches, int factor_kind, int setup_variant) {
     const int nblk = n_pad / kBlk;
     GPD_CUDA(cudaMemsetAsync(dense_tmp, 0, sizeof(double) * (size_t)n_pad * n_pad, s));
     if (factor_kind == 1) {
@@ -482,7 +482,10 @@ int launch_invert_and_pack(cudaStream_t s, const double* L_dev, int n, int n_pad
         diag_inv_kernel<<<nblk, kBlk, 0, s>>>(L_dev, n, n_pad, dense_tmp);
         GPD_CUDA(cudaGetLastError());
         *launches += 1;
-        if (nblk > 1) {
+        if (nblk > 1 && setup_variant >= 1) {
+            // recursive doubling on the tensor pipe (kernels_inv.cu)
+            GPD_TRY(launch_invert_offdiag_dmma(s, L_dev, n, n_pad, dense_tmp, launches));
+        } else if (nblk > 1) {
             offdiag_kernel<<<dim3(nblk - 1, 4), 256, 0, s>>>(L_dev, n, n_pad, nblk, dense_tmp);
             GPD_CUDA(cudaGetLastError());
             *launches += 1;

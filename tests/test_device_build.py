@@ -188,3 +188,65 @@ def test_build_and_loglik_error_paths(gpu_ctx):
         gdisc._loglik(np.zeros((1, 2)), np.zeros((1, 1, 2)), np.zeros((1, 1, 2, 2)))
     lpz, _ = gdisc._loglik(np.zeros((1, 2)), np.zeros((1, 1, 2)), np.tile(np.eye(2), (1, 1, 1, 1)))
     assert np.isfinite(lpz[0, 0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('n', [129, 300, 640, 1000, 2100])
+def test_setup_variants_agree(n, gpu_ctx):
+    """Tensor-pipe setup kernels (option setup_variant = 1: recursive-doubling inverse of the factor on DMMA, row-wise
+    Cholesky block / panel kernels, multi-CTA substitutions for alpha) against the round-1 FMA kernels (= 0) on the same
+    data: same factor up to rounding, same predictions.  n covers 2, 3, 5, 8 and 17 row blocks (pairs with a short or
+    missing right half at every level of the recursion)."""
+    from gpdoemd_b200 import GPModel
+    res = {}
+    try:
+        for variant in (0, 1):
+            gpu_ctx.set_option('setup_variant', variant)
+            gms, ds = synthetic.build_models(GPModel, 5, 1, 1, 3, 2, n, 'Matern52', gp_noise=1e-4, build_on_device=True)
+            gm = gms[0]
+            X = synthetic.candidates(4, 300, 3, ds[0]['xlo'], ds[0]['xhi'])
+            post = gm.gps[0][0].posterior
+            M, S = gm.predict(X)
+            res[variant] = (post.woodbury_chol.copy(), post.woodbury_vector[:, 0].copy(), M, S, gm.d2_s2_d_p2(0, X))
+    finally:
+        gpu_ctx.set_option('setup_variant', 1)
+    L0, a0, M0, S0, H0 = res[0]
+    L1, a1, M1, S1, H1 = res[1]
+    assert np.all(np.triu(L1, 1) == 0) and np.all(np.diag(L1) > 0)
+    # both are backward-stable factorisations of the same matrix: entrywise against |L||L^T|
+    bound = np.abs(L0).dot(np.abs(L0).T)
+    assert np.max(np.abs(L1.dot(L1.T) - L0.dot(L0.T)) / bound) < 8 * (n + 1) * U
+    cond = np.linalg.cond(L0) ** 2
+    assert np.linalg.norm(a1 - a0) / np.linalg.norm(a0) < 100 * cond * U
+    g0 = gm.gps[0][0]
+    ystd = float(np.ravel(gm.ystd)[0])
+    vscale = float(g0.kern.kernx.variance * g0.kern.kernp.variance) * ystd ** 2     # k** in original units
+    print('n=%d: cond %.1e, |dalpha| %.1e, mean %.1e, var %.1e, d2s2 %.1e' % (
+        n, cond, np.linalg.norm(a1 - a0) / np.linalg.norm(a0), np.max(np.abs(M1 - M0)) / ystd,
+        np.max(np.abs(S1 - S0)) / vscale, np.max(np.abs(H1 - H0)) / max(float(np.max(np.abs(H0))), 1e-300)))
+    assert np.max(np.abs(M1 - M0)) < 1e-9 * ystd
+    assert np.max(np.abs(S1 - S0)) < 1e-9 * vscale
+    assert np.max(np.abs(H1 - H0)) < 1e-7 * max(float(np.max(np.abs(H0))), 1e-300)
+
+
+@pytest.mark.gpu
+def test_uploaded_factor_inverse_variants_agree(gpu_ctx):
+    """gpd_gp_upload (host factor, the from_reference path) through both inversion kernels"""
+    oms, ds = helpers.oracle_models(7, M=1, E=1, D=3, P=2, n=700, kernel='RBF', gp_noise=1e-4)
+    X = synthetic.candidates(4, 257, 3, ds[0]['xlo'], ds[0]['xhi'])
+    out = {}
+    try:
+        for variant in (0, 1):
+            gpu_ctx.set_option('setup_variant', variant)
+            gm = helpers.gpu_models(oms)[0]
+            out[variant] = gm.predict(X)
+    finally:
+        gpu_ctx.set_option('setup_variant', 1)
+    M0, S0 = oms[0].predict(X)
+    for variant in (0, 1):
+        assert helpers.relerr(out[variant][0], M0, oms[0].ystd) < 1e-9
+    g0 = oms[0].gps[0][0]
+    vscale = float(g0.kern.kernx.variance * g0.kern.kernp.variance) * float(np.ravel(oms[0].ystd)[0]) ** 2
+    for variant in (0, 1):
+        assert helpers.relerr(out[variant][1], S0, vscale) < 1e-9
+    assert np.max(np.abs(out[1][1] - out[0][1])) < 1e-10 * vscale
