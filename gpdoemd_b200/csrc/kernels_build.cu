@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "radial.cuh"
+#include "tri_core.cuh"
 
 namespace gpd {
 
@@ -286,6 +287,7 @@ __global__ void __launch_bounds__(kBlk) chol_diag_rows_kernel(double* __restrict
     const int r0 = J * kBlk, bs = min(kBlk, n - r0);
     const int i = threadIdx.x;
     // rows/columns >= bs are identity padding, so the loops below have compile-time bounds
+#pragma unroll 16                                                  // 16 independent row loads in flight
     for (int r = 0; r < kBlk; ++r) {
         double v = (r == i) ? 1.0 : 0.0;
         if (r < bs && i < bs) v = (i <= r) ? A[(size_t)(r0 + r) * n + r0 + i] : 0.0;   // coalesced rows of the lower triangle
@@ -332,29 +334,30 @@ __global__ void __launch_bounds__(kBlk) chol_diag_rows_kernel(double* __restrict
         if (i <= r) A[(size_t)(r0 + r) * n + r0 + i] = S[r * kCholLd + i];
 }
 
-// panel rows below the diagonal block:  X L_JJ^T = A_IJ, one thread per row, 32 rows per CTA, no barriers in the
-// substitution.  Finished columns of a row live in shared memory (column-major, conflict-free), the current 16 in
-// registers.
-constexpr int kPanelRows2 = 32;
+// panel rows below the diagonal block:  X L_JJ^T = A_IJ, one thread per row, 64 rows per CTA, no barriers in the
+// substitution.  The CTA's rows are staged column-major in shared memory (conflict-free) and overwritten in place by
+// the solution; the current 16 columns of a row live in registers.  All 128 threads load and store, 64 substitute.
+constexpr int kPanelRows2 = 64;
 constexpr int kPanelLd2 = kPanelRows2 + 1;
 
-__global__ void __launch_bounds__(kPanelRows2) chol_panel_rows_kernel(double* __restrict__ A, int n, int J) {
+__global__ void __launch_bounds__(kBlk) chol_panel_rows_kernel(double* __restrict__ A, int n, int J) {
     extern __shared__ double sm[];
     double* Ls = sm;                          // [128][kCholLd] L_JJ (lower), row c = coefficients of column c of X
-    double* Xs = sm + kBlk * kCholLd;         // [128][kPanelLd2] finished columns of this CTA's rows
+    double* Xs = sm + kBlk * kCholLd;         // [128][kPanelLd2] this CTA's rows, column-major
     const int c0g = J * kBlk;
     const int row0 = (J + 1) * kBlk + blockIdx.x * kPanelRows2;
     const int nrows = min(kPanelRows2, n - row0);
     const int t = threadIdx.x;
-    for (int r = 0; r < kBlk; ++r)
-        for (int cc = t; cc < kBlk; cc += kPanelRows2) Ls[r * kCholLd + cc] = (cc <= r) ? A[(size_t)(c0g + r) * n + c0g + cc] : 0.0;
+#pragma unroll 16
+    for (int r = 0; r < kBlk; ++r) Ls[r * kCholLd + t] = (t <= r) ? A[(size_t)(c0g + r) * n + c0g + t] : 0.0;
+#pragma unroll 16
+    for (int r = 0; r < kPanelRows2; ++r) Xs[t * kPanelLd2 + r] = (r < nrows) ? A[(size_t)(row0 + r) * n + c0g + t] : 0.0;
     __syncthreads();
     if (t < nrows) {
-        const double* __restrict__ arow = A + (size_t)(row0 + t) * n + c0g;
         for (int c0 = 0; c0 < kBlk; c0 += kSlice) {
             double p[kSlice];
 #pragma unroll
-            for (int j = 0; j < kSlice; ++j) p[j] = arow[c0 + j];
+            for (int j = 0; j < kSlice; ++j) p[j] = Xs[(c0 + j) * kPanelLd2 + t];
             for (int m = 0; m < c0; ++m) {
                 const double xm = Xs[m * kPanelLd2 + t];
 #pragma unroll
@@ -371,34 +374,76 @@ __global__ void __launch_bounds__(kPanelRows2) chol_panel_rows_kernel(double* __
         }
     }
     __syncthreads();
-    for (int r = 0; r < nrows; ++r)                               // coalesced row stores
-        for (int cc = t; cc < kBlk; cc += kPanelRows2) A[(size_t)(row0 + r) * n + c0g + cc] = Xs[cc * kPanelLd2 + r];
+    for (int r = 0; r < nrows; ++r) A[(size_t)(row0 + r) * n + c0g + t] = Xs[t * kPanelLd2 + r];   // coalesced row stores
 }
 
 // ---- alpha = L^-T (L^-1 y) as blocked substitution over many CTAs: per diagonal block one small solve kernel and
 // one update kernel for the rest of the vector (dpotrs order of operations inside a block) ----
 __global__ void __launch_bounds__(kBlk) solve_diag_kernel(const double* __restrict__ L, int n, int J, int transposed,
                                                           double* __restrict__ x) {
+    // 128 unknowns as 4 warp blocks of 32: the owning warp solves its 32 x 32 triangle column by column with shuffles
+    // (no CTA barrier), then the remaining warps subtract that block's contribution: 2 CTA barriers per warp block
+    // instead of 2 per column.  Rows / columns >= bs are identity padding.
     extern __shared__ double S[];   // [128][kCholLd]
     __shared__ double xb[kBlk];
     const int r0 = J * kBlk, bs = min(kBlk, n - r0);
-    const int i = threadIdx.x;
-    for (int r = 0; r < bs; ++r)
-        if (i < bs) S[r * kCholLd + i] = (i <= r) ? L[(size_t)(r0 + r) * n + r0 + i] : 0.0;
-    if (i < bs) xb[i] = x[r0 + i];
+    const int i = threadIdx.x, warp = i >> 5, lane = i & 31;
+#pragma unroll 16
+    for (int r = 0; r < kBlk; ++r) {
+        double v = (r == i) ? 1.0 : 0.0;
+        if (r < bs && i < bs) v = (i <= r) ? L[(size_t)(r0 + r) * n + r0 + i] : 0.0;
+        S[r * kCholLd + i] = v;
+    }
+    xb[i] = i < bs ? x[r0 + i] : 0.0;
     __syncthreads();
     if (!transposed) {
-        for (int c = 0; c < bs; ++c) {
-            if (i == c) xb[c] /= S[c * kCholLd + c];
+        for (int b = 0; b < 4; ++b) {
+            if (warp == b) {
+                double xi = xb[i];
+                const double dii = S[i * kCholLd + i];
+#pragma unroll 8
+                for (int c = 0; c < 32; ++c) {
+                    if (lane == c) xi = xi / dii;
+                    const double xc = __shfl_sync(0xffffffffu, xi, c);
+                    if (lane > c) xi = fma(-S[i * kCholLd + b * 32 + c], xc, xi);
+                }
+                xb[i] = xi;
+            }
             __syncthreads();
-            if (i > c && i < bs) xb[i] = fma(-S[i * kCholLd + c], xb[c], xb[i]);
+            if (warp > b) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+                for (int c = 0; c < 32; c += 2) {
+                    s0 = fma(S[i * kCholLd + b * 32 + c], xb[b * 32 + c], s0);
+                    s1 = fma(S[i * kCholLd + b * 32 + c + 1], xb[b * 32 + c + 1], s1);
+                }
+                xb[i] -= s0 + s1;
+            }
             __syncthreads();
         }
     } else {
-        for (int c = bs - 1; c >= 0; --c) {
-            if (i == c) xb[c] /= S[c * kCholLd + c];
+        for (int b = 3; b >= 0; --b) {
+            if (warp == b) {
+                double xi = xb[i];
+                const double dii = S[i * kCholLd + i];
+#pragma unroll 8
+                for (int c = 31; c >= 0; --c) {
+                    if (lane == c) xi = xi / dii;
+                    const double xc = __shfl_sync(0xffffffffu, xi, c);
+                    if (lane < c) xi = fma(-S[(b * 32 + c) * kCholLd + i], xc, xi);   // (L^T)[i][c] = L[c][i]
+                }
+                xb[i] = xi;
+            }
             __syncthreads();
-            if (i < c) xb[i] = fma(-S[c * kCholLd + i], xb[c], xb[i]);   // (L^T)[i][c] = L[c][i]
+            if (warp < b) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+                for (int c = 0; c < 32; c += 2) {
+                    s0 = fma(S[(b * 32 + c) * kCholLd + i], xb[b * 32 + c], s0);
+                    s1 = fma(S[(b * 32 + c + 1) * kCholLd + i], xb[b * 32 + c + 1], s1);
+                }
+                xb[i] -= s0 + s1;
+            }
             __syncthreads();
         }
     }
@@ -440,6 +485,73 @@ __global__ void __launch_bounds__(256) solve_update_bwd_kernel(const double* __r
     x[i] -= s0 + s1;
 }
 
+// trailing update on the tensor pipe: 128 x 128 tiles (ti >= tj) of the rows / columns below block J,
+//   A[ti][tj] -= A[ti][J] * A[tj][J]^T      (k extent 128, mma.sync m8n8k4 f64; 16 warps as 2 x 8, 64 x 16 warp tiles)
+constexpr int kUpdLdA = 20, kUpdLdB = 132;   // bank-conflict-free fragment reads, see kernels_inv.cu
+
+__global__ void __launch_bounds__(512, 1) chol_update_dmma_kernel(double* __restrict__ A, int n, int J) {
+    const int tj = blockIdx.x, ti = blockIdx.y;
+    if (tj > ti) return;
+    __shared__ __align__(16) double As[kBlk * kUpdLdA];
+    __shared__ __align__(16) double Bs[kChunkK * kUpdLdB];
+    const int base = (J + 1) * kBlk, c0 = J * kBlk;
+    const int i0 = base + ti * kBlk, j0 = base + tj * kBlk;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 3, wn = warp & 7, lq = lane & 3, lr = lane >> 2;
+    double acc[8][2][2];
+#pragma unroll
+    for (int mb = 0; mb < 8; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+    const int ar = tid >> 2, ak = (tid & 3) * 4;    // both operands: row ar of the tile, k ak .. ak+3 of the 16-k stage
+    double ra[4], rb[4];
+    auto fetch = [&](int step) {
+        const int gi = i0 + ar, gj = j0 + ar;
+        const double* __restrict__ pa = A + (size_t)gi * n + c0 + step * kChunkK + ak;
+        const double* __restrict__ pb = A + (size_t)gj * n + c0 + step * kChunkK + ak;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            ra[q] = gi < n ? pa[q] : 0.0;
+            rb[q] = gj < n ? pb[q] : 0.0;
+        }
+    };
+    fetch(0);
+#pragma unroll 1
+    for (int step = 0; step < kChunksPerBlk; ++step) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            As[ar * kUpdLdA + ak + q] = ra[q];
+            Bs[(ak + q) * kUpdLdB + ar] = rb[q];               // transposed: Bs[k][column of the output tile]
+        }
+        __syncthreads();
+        if (step + 1 < kChunksPerBlk) fetch(step + 1);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            double av[8], bv[2];
+#pragma unroll
+            for (int mb = 0; mb < 8; ++mb) av[mb] = As[(wm * 64 + mb * 8 + lr) * kUpdLdA + ks * 4 + lq];
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) bv[nb] = Bs[(ks * 4 + lq) * kUpdLdB + wn * 16 + nb * 8 + lr];
+#pragma unroll
+            for (int mb = 0; mb < 8; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], av[mb], bv[nb]);
+        }
+    }
+#pragma unroll
+    for (int mb = 0; mb < 8; ++mb) {
+        const int gi = i0 + wm * 64 + mb * 8 + lr;
+        if (gi >= n) continue;
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+            const int gj = j0 + wn * 16 + nb * 8 + 2 * lq;
+            if (gj <= gi) A[(size_t)gi * n + gj] -= acc[mb][nb][0];
+            if (gj + 1 <= gi) A[(size_t)gi * n + gj + 1] -= acc[mb][nb][1];
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
@@ -476,12 +588,17 @@ int launch_cholesky(cudaStream_t s, double* A_dev, int n, int* info_dev, uint64_
         const int below = n - (J + 1) * kBlk;
         if (below <= 0) break;
         if (setup_variant >= 1)
-            chol_panel_rows_kernel<<<(below + kPanelRows2 - 1) / kPanelRows2, kPanelRows2, panel_smem2, s>>>(A_dev, n, J);
+            chol_panel_rows_kernel<<<(below + kPanelRows2 - 1) / kPanelRows2, kBlk, panel_smem2, s>>>(A_dev, n, J);
         else
             chol_panel_kernel<<<(below + kPanelRows - 1) / kPanelRows, kPanelRows, panel_smem, s>>>(A_dev, n, J);
         GPD_CUDA(cudaGetLastError());
-        const int t = (below + kUpd - 1) / kUpd;
-        chol_update_kernel<<<dim3(t, t), 256, 0, s>>>(A_dev, n, J);
+        if (setup_variant >= 1) {
+            const int t2 = (below + kBlk - 1) / kBlk;
+            chol_update_dmma_kernel<<<dim3(t2, t2), 512, 0, s>>>(A_dev, n, J);
+        } else {
+            const int t = (below + kUpd - 1) / kUpd;
+            chol_update_kernel<<<dim3(t, t), 256, 0, s>>>(A_dev, n, J);
+        }
         GPD_CUDA(cudaGetLastError());
         *launches += 2;
     }
