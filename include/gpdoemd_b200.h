@@ -100,7 +100,9 @@ int  gpd_set_scratch_bytes(gpd_ctx* ctx, uint64_t bytes);
  * "head_periods" 0 (default) .. 16 / "head_grid" 0 (all SMs) or a CTA count: a longer tail-overlap head on a restricted
  *   grid (measured neutral on C2);
  * "tri_parts" 0 (default) = whole work items, 1..8 = every (GP, tile) item of the first-order contraction cut into that
- *   many row-block parts, 9 = by factor size (measured slower at n = 4000, kept for experiments) */
+ *   many row-block parts, 9 = by factor size (measured slower at n = 4000, kept for experiments);
+ * "setup_variant" 1 (default) = per-GP setup (gpd_gp_upload / gpd_gp_build) with the factor inverse and the Cholesky
+ *   trailing update on the FP64 tensor pipe, 0 = the round-1 FP64 FMA kernels (A/B tests) */
 int  gpd_set_option(gpd_ctx* ctx, const char* name, int64_t value);
 /* number of CUDA kernels launched by this context so far (bench.py `gpu_launches`) */
 uint64_t gpd_launch_count(gpd_ctx* ctx);
