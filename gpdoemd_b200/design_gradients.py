@@ -9,13 +9,13 @@ rule through the closed-form criteria of ``design_criteria.py:49-144`` for the h
 
     f, g = criterion_gradient('BH', mu, S, dmu, dS, noise_var, pps)      # f (K,), g (K, D)
 
-with mu (K,M,E), S (K,M,E,E), dmu (K,M,E,D), dS (K,M,E,E,D).  HR, BH, BF and AW are covered; JR is not (its
-refinement uses the derivative-free search)."""
+with mu (K,M,E), S (K,M,E,E), dmu (K,M,E,D), dS (K,M,E,E,D).  All five criteria are covered (first-order marginals;
+second-order refinement uses the derivative-free search)."""
 import numpy as np
 
 from .design_criteria import _reshape
 
-SUPPORTED = ('HR', 'BH', 'BF', 'AW')
+SUPPORTED = ('HR', 'BH', 'BF', 'AW', 'JR')
 
 
 def _quad_and_grad(iS, dS, r, dr):
@@ -24,6 +24,43 @@ def _quad_and_grad(iS, dS, r, dr):
     q = np.einsum('ka,ka->k', r, w)
     dq = 2.0 * np.einsum('ka,kad->kd', w, dr) - np.einsum('ka,kabd,kb->kd', w, dS, w)
     return q, dq
+
+
+def _jensen_renyi(mu, Sn, dmu, dS, pps, E):
+    """JR (design_criteria.py:147-194) and its x-gradient.  With P_i = S_i^-1, l_i = log|S_i|:
+        T1 = sum_i pi_i (E/2 log 4 pi + l_i / 2),   T2 = sum_i pi_i^2 2^(-E/2) |S_i|^(-1/2) + 2 sum_{i<j} pi_i pi_j e^(-phi_ij/2),
+        phi_ij = mu_i'P_i mu_i + mu_j'P_j mu_j - m'(P_i+P_j)^-1 m + l_i + l_j + log|P_i+P_j|,   m = P_i mu_i + P_j mu_j,
+        JR = E/2 log 2 pi - log T2 - T1;   dP = -P dS P,  dl = tr(P dS),  d log|R| = tr(R^-1 dR),  dR^-1 = -R^-1 dR R^-1."""
+    K, M = mu.shape[:2]
+    P = np.linalg.inv(Sn)
+    ld = np.log(np.linalg.det(Sn))                                            # (K, M)
+    dl = np.einsum('kmab,kmbad->kmd', P, dS)
+    dP = -np.einsum('kmab,kmbcd,kmce->kmaed', P, dS, P)                       # (K, M, E, E, D)
+    Pm = np.einsum('kmab,kmb->kma', P, mu)
+    a = np.einsum('kma,kma->km', mu, Pm)
+    da = 2.0 * np.einsum('kma,kmad->kmd', Pm, dmu) - np.einsum('kma,kmabd,kmb->kmd', Pm, dS, Pm)
+    dPm = np.einsum('kmabd,kmb->kmad', dP, mu) + np.einsum('kmab,kmbd->kmad', P, dmu)
+    T1 = np.sum(pps * (0.5 * E * np.log(4.0 * np.pi) + 0.5 * ld), axis=1)
+    dT1 = 0.5 * np.einsum('m,kmd->kd', pps, dl)
+    root = np.exp(-0.5 * ld) * 2.0 ** (-0.5 * E)                              # 2^(-E/2) |S_i|^(-1/2)
+    T2 = np.sum(pps * pps * root, axis=1)
+    dT2 = np.einsum('m,km,kmd->kd', pps * pps, -0.5 * root, dl)
+    for i in range(M - 1):
+        for j in range(i + 1, M):
+            R, dR = P[:, i] + P[:, j], dP[:, i] + dP[:, j]
+            Q = np.linalg.inv(R)
+            m, dm = Pm[:, i] + Pm[:, j], dPm[:, i] + dPm[:, j]
+            u = np.einsum('kab,kb->ka', Q, m)
+            b = np.einsum('ka,ka->k', m, u)
+            db = 2.0 * np.einsum('ka,kad->kd', u, dm) - np.einsum('ka,kabd,kb->kd', u, dR, u)
+            c = np.log(np.linalg.det(R))
+            dc = np.einsum('kab,kbad->kd', Q, dR)
+            phi = a[:, i] + a[:, j] - b + ld[:, i] + ld[:, j] + c
+            dphi = da[:, i] + da[:, j] - db + dl[:, i] + dl[:, j] + dc
+            e = 2.0 * pps[i] * pps[j] * np.exp(-0.5 * phi)
+            T2 += e
+            dT2 += e[:, None] * (-0.5 * dphi)
+    return 0.5 * E * np.log(2.0 * np.pi) - np.log(T2) - T1, -dT2 / T2[:, None] - dT1
 
 
 def criterion_gradient(kind, mu, S, dmu, dS, noise_var=None, pps=None):
@@ -71,6 +108,8 @@ def criterion_gradient(kind, mu, S, dmu, dS, noise_var=None, pps=None):
                 f += np.einsum('ab,kba->k', noise, iA) + q
                 g += -np.einsum('kab,kbad->kd', B, dA) + dq
         return f, g
+    if kind == 'JR':
+        return _jensen_renyi(mu, Sn, dmu, dS, pps, E)
     # AW  :126-144
     for i in range(M):
         w = np.zeros(K)

@@ -124,7 +124,7 @@ def score_designs_dev(models, X_dev, N, order=1, criterion='BH', noise_var=None,
 def criterion_with_gradient(models, X, criterion='BH', noise_var=None, pps=None):
     """Criterion value and its gradient with respect to the design at the rows of X (first-order Taylor marginals):
     ``-> f (K,), g (K, D)``.  Device: ``gpd_marginal_dx`` per rival model; host: the chain rule through the criterion
-    (design_gradients.py).  HR, BH, BF, AW."""
+    (design_gradients.py).  HR, BH, BF, AW, JR."""
     from .design_gradients import criterion_gradient
     from .marginal import taylor_first_order_dx
     X = np.array(X, dtype=float, ndmin=2)
@@ -168,11 +168,11 @@ def refine_designs(models, X_start, criterion='BH', order=1, noise_var=None, pps
                    step=None, iters=25, shrink=0.5, tol=1e-6, scorer=None, method='auto', value_and_grad=None):
     """Continuous refinement of the best grid designs.
 
-    method='lbfgs' (default for first order + HR/BH/BF/AW): bound-constrained L-BFGS on the analytic design gradient
+    method='lbfgs' (default for first order, all five criteria): bound-constrained L-BFGS on the analytic design gradient
     (``criterion_with_gradient``: x-derivatives of mu and S on the device, chain rule through the criterion on the
     host), all start points in one batch per iteration; the result of every point is then re-scored by the fused
     scorer and kept only if it improves on its start, and a short compass search polishes it.  method='compass'
-    (JR, second order): the batched derivative-free pattern search described below.
+    (second order): the batched derivative-free pattern search described below.
 
     The reference only evaluates a fixed candidate set and takes ``np.argmax`` (demos/case_study.py:279-293).  Here
     every start point (e.g. the top-k designs of the grid) is improved by polling the 2 * D axis neighbours at the

@@ -1,6 +1,6 @@
 """Design gradients.  Parity = central finite differences of the ORACLE:
 
-* CPU: the chain rule through HR / BH / BF / AW (design_gradients.criterion_gradient) against finite differences of
+* CPU: the chain rule through HR / BH / BF / AW / JR (design_gradients.criterion_gradient) against finite differences of
   the oracle's criteria on an analytic family mu(x), S(x); the L-BFGS refinement loop with an injected objective;
 * GPU: gpd_marginal_dx (mu, S, dmu/dx, dS/dx of the first-order Taylor marginal) against central differences of the
   oracle's taylor_first_order at h = 1e-6, for every kernel class and with a binary design variable; the criterion
@@ -30,7 +30,7 @@ def _family(rng, K, M, E, D):
     return f, dmu, dS
 
 
-@pytest.mark.parametrize('kind', ['HR', 'BH', 'BF', 'AW'])
+@pytest.mark.parametrize('kind', ['HR', 'BH', 'BF', 'AW', 'JR'])
 def test_chain_rule_against_finite_differences_of_the_oracle_criteria(kind):
     rng = np.random.default_rng(3)
     K, M, E, D = 7, 3, 2, 3
@@ -51,6 +51,27 @@ def test_chain_rule_against_finite_differences_of_the_oracle_criteria(kind):
         mm, Sm = fam(Xm)
         fd = (ocrit.CRITERIA[kind](mp, Sp, noise, pps) - ocrit.CRITERIA[kind](mm, Sm, noise, pps)) / (2 * h)
         assert helpers.relerr(g[:, d], fd, np.abs(fd).max()) < 1e-7, (kind, d)
+
+
+@pytest.mark.parametrize('shape', [(5, 5, 1, 2), (4, 4, 3, 3), (3, 2, 4, 2)])
+def test_chain_rule_other_shapes(shape):
+    """the demo shape (M = 5 rival models, one output) and larger E, every criterion, random prior probabilities"""
+    K, M, E, D = shape
+    rng = np.random.default_rng(K * M + E)
+    fam, dmu, dS = _family(rng, K, M, E, D)
+    X = rng.uniform(-1, 1, (K, D))
+    noise, pps = 0.05 * np.eye(E), rng.uniform(0.1, 1, M)
+    mu, S = fam(X)
+    for kind in ('HR', 'BH', 'BF', 'AW', 'JR'):
+        f, g = criterion_gradient(kind, mu, S, dmu, dS, noise, pps)
+        assert helpers.relerr(f, ocrit.CRITERIA[kind](mu, S.copy(), noise, pps)) < 1e-12
+        for d in range(D):
+            h = 1e-6
+            Xp, Xm = X.copy(), X.copy()
+            Xp[:, d] += h
+            Xm[:, d] -= h
+            fd = (ocrit.CRITERIA[kind](*fam(Xp), noise, pps) - ocrit.CRITERIA[kind](*fam(Xm), noise, pps)) / (2 * h)
+            assert helpers.relerr(g[:, d], fd, np.abs(fd).max()) < 1e-7, (kind, d)
 
 
 def test_lbfgs_refinement_host_logic():
@@ -109,7 +130,7 @@ def test_marginal_dx_against_central_differences_of_the_oracle(kernel, nb, gpu_c
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('crit', ['HR', 'BH', 'BF', 'AW'])
+@pytest.mark.parametrize('crit', ['HR', 'BH', 'BF', 'AW', 'JR'])
 def test_criterion_gradient_end_to_end(crit, gpu_ctx):
     import gpdoemd_b200 as g
     oms, ds = helpers.oracle_models(83, M=3, E=2, D=2, P=2, n=120, kernel='Matern52', gp_noise=1e-4)
@@ -150,6 +171,10 @@ def test_lbfgs_refinement_on_the_device(gpu_ctx):
     print('BH: grid %.6g  compass %.6g (%d evaluations)  lbfgs %.6g (%d evaluations)' % (bv, fc[0], ec, fl[0], el))
     assert fl[0] >= bv and fl[0] >= fc[0] * (1 - 1e-6)
     assert np.all((Xl >= lo - 1e-12) & (Xl <= hi + 1e-12)) and set(Xl[:, 2]) <= {0.0, 1.0}
-    # JR has no analytic gradient here: the default falls back to the compass search
-    Xj, fj, _ = refine_designs(gms, top[:2], criterion='JR', noise_var=0.01, bounds=(lo, hi), binary=(2,), iters=5)
-    assert np.all(np.isfinite(fj))
+    # JR: analytic gradient as well (default method), never worse than the start points and than the compass search
+    bj, vj, dcj = g.score_designs(gms, grid, order=1, criterion='JR', noise_var=0.01)
+    topj = grid[np.argsort(-dcj)[:4]]
+    Xj, fj, ej = refine_designs(gms, topj, criterion='JR', noise_var=0.01, bounds=(lo, hi), binary=(2,), iters=30)
+    Xjc, fjc, ejc = refine_designs(gms, topj, criterion='JR', noise_var=0.01, bounds=(lo, hi), binary=(2,), iters=30, method='compass')
+    print('JR: grid %.6g  compass %.6g (%d evaluations)  lbfgs %.6g (%d evaluations)' % (vj, fjc[0], ejc, fj[0], ej))
+    assert np.all(np.isfinite(fj)) and fj[0] >= vj and fj[0] >= fjc[0] * (1 - 1e-6)
