@@ -116,11 +116,14 @@ struct EvalSmem {
 };
 
 template <int KERN, int NXB, int NCB, int CPT, int RG, int MODE, bool ONE_RHS>
+#ifndef GPD_EVAL_TPSM
+#define GPD_EVAL_TPSM 512         // resident threads per SM the small-bucket kernels are compiled for (640 / 768: measured, see profiles)
+#endif
 #ifndef GPD_EVAL_CPT_MID
 #define GPD_EVAL_CPT_MID 4        // candidates per thread of the 11-column bucket (first order with P = 6..10)
 #define GPD_EVAL_MINB_MID 1       // resident CTAs per SM the compiler must allow for it
 #endif
-__global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? 512 : 1024) / (RG * (kBlk / CPT)) : (NCB <= 11 ? GPD_EVAL_MINB_MID : 1)) eval_kernel(const GpView* __restrict__ gps, const Item* __restrict__ items,
+__global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? GPD_EVAL_TPSM : 1024) / (RG * (kBlk / CPT)) : (NCB <= 11 ? GPD_EVAL_MINB_MID : 1)) eval_kernel(const GpView* __restrict__ gps, const Item* __restrict__ items,
                                                             const double* __restrict__ X, int ldx, int chunk_n, int nrhs,
                                                             int ncols, double* __restrict__ panels,
                                                             const double* __restrict__ beta_panels,
