@@ -64,10 +64,27 @@ __device__ __forceinline__ double exp_neg_tab_units(double t, const double* __re
     return (ht - 0x410F8F17u <= 0x7FF00000u - 0x410F8F17u) ? 0.0 : v;
 }
 
+// sqrt(x) for x in [kTinyR2, 1e300], branch-free: hardware reciprocal-square-root estimate (MUFU.RSQ64H, ~2^-20) and two
+// coupled Newton / Goldschmidt steps (error 2^-20 -> 2^-39 -> below one ulp; result within ~1 ulp, not correctly rounded).
+// The library sqrt() carries a slow-path CALL behind a branch per call, which cut the unrolled pair loop of the Matern /
+// Exponential kernels into one basic block per pair; the squared distance is started from kTinyR2 instead of 0 so that the
+// estimate never sees 0 (r = 1e-150 at an exact coincidence changes nothing below 1e-150).
+constexpr double kTinyR2 = 1e-300;
+__device__ __forceinline__ double sqrt_fast_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;
+    double e = fma(-g, h, 0.5);
+    g = fma(g, e, g);
+    h = fma(h, e, h);
+    e = fma(-g, h, 0.5);
+    return fma(g, e, g);
+}
+
 template <int KERN>
 __device__ __forceinline__ double kappa_of_r2(double r2, double power, const double* __restrict__ tab) {
     if (KERN == 0) return exp_neg_tab_units(r2, tab);            // RBF: r2 is already (r^2 / 2) * 256 / ln 2
-    double r = sqrt(r2);
+    double r = sqrt_fast_pos(r2);
     if (KERN == 1) return exp_neg_fast(r, tab);                  // Exponential
     if (KERN == 2) {                                             // Matern32
         const double s3 = 1.7320508075688772;
@@ -283,7 +300,7 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? GP
 #pragma unroll
                     for (int d = 0; d < NXB; ++d) r2 = fma(xs[j][d], xr[d], r2);   // xr = -2 X_i
                 } else {
-                    r2 = 0.0;
+                    r2 = (KERN == 5) ? 0.0 : kTinyR2;            // RatQuad uses r^2 itself, the others take sqrt_fast_pos
 #pragma unroll
                     for (int d = 0; d < NXB; ++d) {
                         const double df = xs[j][d] - xr[d];

@@ -94,7 +94,7 @@ __device__ __forceinline__ void fused_eval(const GpView& g, const FusedArgs& a, 
             double kap[CPT];
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
-                double r2 = 0.0;
+                double r2 = (KERN == 0 || KERN == 5) ? 0.0 : kTinyR2;   // sqrt_fast_pos never sees 0 (eval_impl.cuh)
 #pragma unroll
                 for (int d = 0; d < NXB; ++d) {
                     const double df = xs[j][d] - rv[d];
