@@ -353,7 +353,7 @@ static int plan_build(gpd_ctx* c, gpd_model* const* models, int M, int flags, lo
     int kinds = pl.max_nrhs + (pl.need_W ? pl.max_nrhs : 0) + ((flags & WANT_D2S2) ? 1 : 0);
     pl.fixed_bytes = 0;
     if (pl.fused) {
-        pl.fixed_bytes = sizeof(double) * (size_t)pl.priv_stride * kFusedCtasPerSm * c->num_sms + sizeof(FItem) * 16 * (size_t)c->num_sms + (1 << 16);
+        pl.fixed_bytes = sizeof(double) * (size_t)pl.priv_stride * (c->fused == 2 ? 2 : kFusedCtasPerSm) * c->num_sms + sizeof(FItem) * 16 * (size_t)c->num_sms + (1 << 16);
         extra_fixed += pl.fixed_bytes;
         per_cand += (2 * sizeof(FItem) * pl.entries.size() + kBlk - 1) / kBlk; // one Item per (GP, tile)
     } else per_cand += (size_t)pl.panel_unit * kinds * sizeof(double);
@@ -483,7 +483,7 @@ static int plan_materialize(gpd_ctx* c, Plan& pl, Bump& bump) {
         raws[m] = b.raw;
     }
     const size_t panel_doubles = pl.fused ? 0 : (size_t)pl.panel_unit * Nc;
-    pl.priv = pl.fused ? bump.take<double>((size_t)pl.priv_stride * kFusedCtasPerSm * c->num_sms) : nullptr;
+    pl.priv = pl.fused ? bump.take<double>((size_t)pl.priv_stride * (c->fused == 2 ? 2 : kFusedCtasPerSm) * c->num_sms) : nullptr;
     pl.fitems_dev = pl.fused ? bump.take<FItem>(fitems.size()) : nullptr;
     pl.panels_in = bump.take<double>(panel_doubles * pl.max_nrhs);
     pl.panels_out = pl.need_W ? bump.take<double>(panel_doubles * pl.max_nrhs) : nullptr;
@@ -686,9 +686,10 @@ static int run_chunk(gpd_ctx* c, Plan& pl, double* X_dev, int ldx, int nc, const
             fa.ncols = ncols;
             fa.ng = 2 * pl.fused_parts;
             fa.trim = c->tri_trim;
-            const int grid = std::min(grp.fitem_count, kFusedCtasPerSm * c->num_sms);
+            const int grid = std::min(grp.fitem_count, (c->fused == 2 ? 1 : kFusedCtasPerSm) * c->num_sms);
             Span sp(c, F_TRI, 1, fl);
-            const int rc = launch_fused(s, grp.kernel, grid, grp.nx, ncols, fa);
+            const int rc = c->fused == 2 ? launch_fusedc(s, grp.kernel, grid, grp.nx, ncols, fa)
+                                         : launch_fused(s, grp.kernel, grid, grp.nx, ncols, fa);
             GPD_CHECK(rc >= 0, "internal: no fused kernel variant for a shape the planner accepted");
             if (rc) return rc;
         }
@@ -934,7 +935,7 @@ int gpd_set_option(gpd_ctx* c, const char* name, int64_t value) {
         return 0;
     }
     if (!strcmp(name, "fused")) {
-        GPD_CHECK(value == 0 || value == 1, "fused is 0 or 1");
+        GPD_CHECK(value >= 0 && value <= 2, "fused is 0, 1 (phase-serial fused kernel) or 2 (producer warps inside the contraction CTA)");
         c->fused = (int)value;
         return 0;
     }

@@ -169,6 +169,7 @@ int launch_gram(cudaStream_t s, const GpView* gps_dev, const Item* items_dev, in
 int launch_dmma_probe(cudaStream_t s, int num_sms, int iters, double* sink_dev);
 // kernels_fused.cu: K1 + K2 in one persistent kernel (first-order path); returns -1 when no variant covers the shape
 int launch_fused(cudaStream_t s, int kernel, int grid, int nx, int ncols, const FusedArgs& args);
+int launch_fusedc(cudaStream_t s, int kernel, int grid, int nx, int ncols, const FusedArgs& args);   // two private panels per CTA
 // kernels_xgrad.cu
 int launch_xgrad_eval(cudaStream_t s, const GpView* gps_dev, int ngp, int tiles, const double* X_dev, int ldx, int chunk_n,
                       double* panels, double* acc);

@@ -1,0 +1,7 @@
+// concurrent evaluation + triangular contraction, kernel class 3 (see fusedc_impl.cuh); one translation unit per class
+// so that the variants compile in parallel
+#include "fusedc_impl.cuh"
+
+namespace gpd {
+GPD_DEFINE_FUSEDC_TU(3)
+}  // namespace gpd

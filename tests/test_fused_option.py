@@ -1,7 +1,9 @@
 """Option "fused" (off by default): the first-order path through ONE persistent kernel that evaluates the kernel rows
 into a private L2-resident panel and contracts them in place (csrc/fused_impl.cuh).  Same numbers as the separate
 evaluation + triangular kernels up to the summation order of the mean contractions; the tail-wave items are cut into
-row-block parts, so sizes around one and several waves of the 148-CTA grid are covered."""
+row-block parts, so sizes around one and several waves of the 148-CTA grid are covered.  Variant 2
+(csrc/fusedc_impl.cuh) keeps tri_kernel's consumer structure and adds a producer warpgroup that evaluates the CTA's next
+item concurrently."""
 import numpy as np
 import pytest
 
@@ -22,8 +24,9 @@ CASES = [  # M, E, D, P, n, kernel, n_binary, N
 ]
 
 
+@pytest.mark.parametrize('variant', [1, 2], ids=['serial', 'concurrent'])
 @pytest.mark.parametrize('case', CASES, ids=lambda c: '%s-n%d-N%d' % (c[5], c[4], c[7]))
-def test_fused_kernel_matches_the_separate_kernels_and_the_oracle(case, gpu_ctx):
+def test_fused_kernel_matches_the_separate_kernels_and_the_oracle(case, variant, gpu_ctx):
     import gpdoemd_b200 as g
     M, E, D, P, n, kernel, nb, N = case
     oms, ds = helpers.oracle_models(7, M=M, E=E, D=D, P=P, n=n, kernel=kernel, n_binary=nb, gp_noise=1e-4)
@@ -34,7 +37,7 @@ def test_fused_kernel_matches_the_separate_kernels_and_the_oracle(case, gpu_ctx)
     out = {}
     try:
         for flag in (0, 1):
-            gpu_ctx.set_option('fused', flag)
+            gpu_ctx.set_option('fused', flag * variant)
             out[flag] = g.score_designs_multi(gms, X, ['HR', 'BH', 'JR'], order=1, noise_var=0.02)
             out[flag]['marg'] = g.taylor_first_order(gms[0], X)
     finally:
