@@ -17,8 +17,8 @@
 // [0, I1 * 128) of item seq into it -- panel[i][t ^ swizzle] = kx_i(x_t) G0_i, mean / derivative contractions to the raw
 // outputs when the item covers the last row block -- then `fence.proxy.async` (the panel is read back by bulk async
 // copies) and arrive on `ready[b]`.  The copy-issuing thread waits on `ready[b]` when its chunk stream enters item seq.
-// Registers: 640 threads are launched at 96 registers; the consumer warpgroups raise their limit to 112 and the
-// producer warpgroup drops to 64 (setmaxnreg), 512 * 112 + 128 * 64 = 64 Ki.
+// Registers: 640 threads are launched at 96 registers; the consumer warpgroups raise their limit to 104 and the
+// producer warpgroup drops to 64 (setmaxnreg), 512 * 104 + 128 * 64 = 640 * 96: the increase is funded by the decrease inside the CTA pool.
 #pragma once
 #include "common.cuh"
 #include "eval_impl.cuh"
@@ -48,6 +48,23 @@ struct FcSmem {
     double rec[kFcRows * FcRec<NXB, NCB>::RS > kBlk * NCB ? kFcRows * FcRec<NXB, NCB>::RS : kBlk * NCB];
 };
 
+// polling wait with back-off: the producers are idle for most of an item and must not spend issue slots on the poll
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        __nanosleep(1000);
+    }
+}
 __device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 2, %0;" ::"n"(kFcProducers) : "memory"); }
 
 // ---- producer warpgroup: panel rows [0, kend) of one item, optional mean contractions --------------------------------
@@ -251,7 +268,7 @@ __global__ void __launch_bounds__(kFcThreads, 1) fusedc_kernel(const FusedArgs a
             if (it.tile * kBlk >= count) continue;         // the consumers skip the same items
             const int I1 = it.I1 ? it.I1 : g.nblk;
             const int buf = seq & 1;
-            mbar_wait(smem_u32(&sm.pfree[buf]), ((seq >> 1) & 1) ^ 1);   // the item that used this buffer is contracted
+            mbar_wait_sleep(smem_u32(&sm.pfree[buf]), ((seq >> 1) & 1) ^ 1);   // the item that used this buffer is contracted
             fc_produce<KERN, NXB, NCB>(g, args, it.tile, count, I1 * kBlk, I1 == g.nblk, priv + (size_t)buf * args.priv_stride,
                                        sm.rec, sm.tab, ptid);
             asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy writes -> bulk async copies
@@ -262,7 +279,7 @@ __global__ void __launch_bounds__(kFcThreads, 1) fusedc_kernel(const FusedArgs a
     }
 
     // =================== consumer warpgroups ===================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     int stage = 0;
     uint32_t phase = 0;
     const bool is_issuer = (threadIdx.x == 0);

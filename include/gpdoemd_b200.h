@@ -93,9 +93,10 @@ int  gpd_set_scratch_bytes(gpd_ctx* ctx, uint64_t bytes);
  * "tail_overlap" 1 (default) = first-order path: the candidate tiles that would form the last, partial wave of the
  *   persistent triangular kernel are evaluated and contracted first, concurrently with the evaluation of the rest;
  * "tri_trim" 1 (default) = the all-padding 8-row blocks (rows n..n_pad) of the last row block are skipped;
- * "fused" 0 (default) / 1 = first-order path through ONE persistent kernel that evaluates the kernel rows into a private
+ * "fused" 0 (default) / 1 / 2 = first-order path through ONE persistent kernel that evaluates the kernel rows into a private
  *   L2-resident panel and contracts them in place: O(SMs * n) scratch instead of O(N * n), measured 1-8 % slower than the
- *   separate kernels;
+ *   separate kernels; 2 = the same with a producer warpgroup evaluating the next item concurrently
+ *   (measured slower still);
  * "scratch_redzones" 0 (default) / 1 = debug red zones behind every scratch sub-buffer, see gpd_debug_check_scratch;
  * "head_periods" 0 (default) .. 16 / "head_grid" 0 (all SMs) or a CTA count: a longer tail-overlap head on a restricted
  *   grid (measured neutral on C2);

@@ -5,6 +5,9 @@ sys.path.insert(0, '.')
 import gpdoemd_b200 as g
 from gpdoemd_b200 import synthetic
 ctx = g.get_context(0)
+import os
+for _o in filter(None, os.environ.get('GPD_OPTIONS', '').split(',')):     # e.g. GPD_OPTIONS=fused=2
+    ctx.set_option(_o.split('=')[0], int(_o.split('=')[1]))
 cfg = dict(synthetic.CONFIGS[sys.argv[1] if len(sys.argv) > 1 else 'C2'])
 if len(sys.argv) > 2:
     cfg['N'] = int(float(sys.argv[2]))
