@@ -63,6 +63,7 @@ struct gpd_ctx {
     int setup_variant = 1;                  // option "setup_variant": 1 = per-GP setup on the tensor pipe (kernels_inv.cu), 0 = round-1 FMA kernels
     uint64_t scratch_limit = 6ull << 30;
     DevBuf scratch, tables, flush;
+    DevBuf setup_a, setup_dense;           // n x n work matrices of gpd_gp_build / gpd_gp_upload, kept between GPs (a model has E x R of them)
     uint64_t launches = 0;
     int tri_variant = 2;   // 0: 16 warps as 4 x 4 (32 x 32 warp tiles), 1: 8 warps as 2 x 4, 2: 16 warps as 2 x 8 (64 x 16)
     int tri_cps = 0;   // 0 = automatic (by factor size), 1 or 2 = forced chunks per pipeline stage
@@ -857,6 +858,8 @@ void gpd_destroy(gpd_ctx* c) {
     c->scratch.release();
     c->tables.release();
     c->flush.release();
+    c->setup_a.release();
+    c->setup_dense.release();
     for (auto& e : c->res_pool) cudaFree(e.first);
     for (auto& s : c->spans) {
         cudaEventDestroy(s.a);
@@ -1216,18 +1219,17 @@ static int gp_create_common(gpd_ctx* c, const gpd_gp_desc* d, gpd_gp** out) {
 
 // L_dev (n x n row-major, lower triangle) -> packed forward / backward operands of the triangular kernel
 static int gp_pack_factor(gpd_ctx* c, gpd_gp* g, const double* L_dev, int factor_kind) {
-    double* dense = nullptr;
-    if (cudaMalloc(&dense, sizeof(double) * (size_t)g->n_pad * g->n_pad) != cudaSuccess) {
+    if (c->setup_dense.ensure(sizeof(double) * (size_t)g->n_pad * g->n_pad)) {
         set_error("out of device memory for the factor inversion workspace");
         return 1;
     }
+    double* dense = static_cast<double*>(c->setup_dense.p);
     uint64_t nl = 0;
     int rc = launch_invert_and_pack(c->stream, L_dev, g->n, g->n_pad, dense, g->LinvF, g->LinvB, &nl, factor_kind,
                                     c->setup_variant);
     c->launches += nl;
     if (c->profile) c->fam_launches[F_SETUP] += nl;
     cudaError_t e = cudaStreamSynchronize(c->stream);
-    cudaFree(dense);
     if (rc) return rc;
     if (e != cudaSuccess) {
         set_error(std::string("factor inversion failed: ") + cudaGetErrorString(e));
@@ -1249,15 +1251,14 @@ int gpd_gp_upload(gpd_ctx* c, const gpd_gp_desc* d, gpd_gp** out) {
     g->factor_kind = d->factor_kind;
     const int n = g->n;
     cudaStream_t s = c->stream;
-    double* L_dev = nullptr;
-    cudaError_t e = cudaMalloc(&L_dev, sizeof(double) * (size_t)n * n);
+    cudaError_t e = c->setup_a.ensure(sizeof(double) * (size_t)n * n) ? cudaErrorMemoryAllocation : cudaSuccess;
+    double* L_dev = static_cast<double*>(c->setup_a.p);
     if (e == cudaSuccess) e = cudaMemcpyAsync(g->alpha, d->alpha, sizeof(double) * n, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(L_dev, d->L, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, s);
     int rc = 0;
     if (e == cudaSuccess) rc = gp_pack_factor(c, g, L_dev, d->factor_kind);
     else set_error(std::string("factor upload failed: ") + cudaGetErrorString(e));
     cudaStreamSynchronize(s);
-    cudaFree(L_dev);
     if (e != cudaSuccess || rc) {
         gpd_gp_free(g);
         return rc ? rc : 1;
@@ -1281,7 +1282,8 @@ int gpd_gp_build(gpd_ctx* c, const gpd_gp_desc* d, const double* Y, double noise
     int* info_dev = nullptr;
     int rc = 0;
     double jitter = 0.0;
-    cudaError_t e = cudaMalloc(&A, sizeof(double) * (size_t)n * n);
+    cudaError_t e = c->setup_a.ensure(sizeof(double) * (size_t)n * n) ? cudaErrorMemoryAllocation : cudaSuccess;
+    A = static_cast<double*>(c->setup_a.p);
     if (e == cudaSuccess) e = cudaMalloc(&Z_dev, sizeof(double) * (size_t)n * dz);
     if (e == cudaSuccess) e = cudaMalloc(&y_dev, sizeof(double) * n);
     if (e == cudaSuccess) e = cudaMalloc(&info_dev, sizeof(int));
@@ -1343,7 +1345,6 @@ int gpd_gp_build(gpd_ctx* c, const gpd_gp_desc* d, const double* Y, double noise
     }
     if (e != cudaSuccess && !rc) set_error(std::string("device GP build failed: ") + cudaGetErrorString(e));
     cudaStreamSynchronize(s);
-    cudaFree(A);
     cudaFree(Z_dev);
     cudaFree(y_dev);
     cudaFree(info_dev);
