@@ -11,6 +11,8 @@ for _o in filter(None, os.environ.get('GPD_OPTIONS', '').split(',')):     # e.g.
 cfg = dict(synthetic.CONFIGS[sys.argv[1] if len(sys.argv) > 1 else 'C2'])
 if len(sys.argv) > 2:
     cfg['N'] = int(float(sys.argv[2]))
+if len(sys.argv) > 3:
+    cfg['kernel'] = sys.argv[3]          # kernel class override, e.g. RatQuad
 if cfg['n'] >= 2000:
     ctx.set_scratch_bytes(64 << 30)
 gms, ds = synthetic.build_models(g.GPModel, 2, cfg['M'], cfg['E'], cfg['D'], cfg['P'], cfg['n'], cfg['kernel'], build_on_device=cfg['n'] >= 2000)
