@@ -14,6 +14,7 @@
 #pragma once
 #include "common.cuh"
 #include "exp2_table.h"
+#include "log_table.h"
 
 namespace gpd {
 
@@ -81,6 +82,36 @@ __device__ __forceinline__ double sqrt_fast_pos(double x) {
     return fma(g, e, g);
 }
 
+// shared-memory tables of one evaluation CTA: 2^(j/256) (kernels 0..3 and 5), then 1 / c_j and ln c_j (kernel 5 only)
+constexpr int kKernTabSize = kExpTabSize + 2 * kLogTabSize;
+template <int KERN>
+__device__ __forceinline__ void load_kernel_tables(double* __restrict__ sTab, int tid, int nthreads) {
+    if (KERN <= 3 || KERN == 5)
+        for (int k = tid; k < kExpTabSize; k += nthreads) sTab[k] = kExp2Tab[k];
+    if (KERN == 5)
+        for (int k = tid; k < kLogTabSize; k += nthreads) {
+            sTab[kExpTabSize + k] = kLogInvTab[k];
+            sTab[kExpTabSize + kLogTabSize + k] = kLogLnTab[k];
+        }
+}
+
+// ln(u) for u in [1, 2^1000], branch-free, absolute error ~ (1 + k) 1e-16: u = 2^k m with m in [1, 2); the top 7 mantissa
+// bits pick c_j, r = m / c_j - 1 (|r| <= 2^-8) and log1p(r) is a degree-6 polynomial (truncation 2e-18).  The library
+// log1p / exp pair of the RatQuad profile carried slow-path CALLs behind branches (one basic block per pair, like sqrt).
+__device__ __forceinline__ double log_ge1_tab(double u, const double* __restrict__ tlog) {
+    const int hi = __double2hiint(u);
+    const int k = (hi >> 20) - 1023;
+    const int j = (hi >> 13) & (kLogTabSize - 1);
+    const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(u));
+    const double r = fma(m, tlog[j], -1.0);
+    double p = fma(r, -1.0 / 6.0, 0.2);
+    p = fma(p, r, -0.25);
+    p = fma(p, r, 1.0 / 3.0);
+    p = fma(p, r, -0.5);
+    p = fma(p, r, 1.0);
+    return fma((double)k, 0.6931471805599453, fma(p, r, tlog[kLogTabSize + j]));
+}
+
 template <int KERN>
 __device__ __forceinline__ double kappa_of_r2(double r2, double power, const double* __restrict__ tab) {
     if (KERN == 0) return exp_neg_tab_units(r2, tab);            // RBF: r2 is already (r^2 / 2) * 256 / ln 2
@@ -97,7 +128,8 @@ __device__ __forceinline__ double kappa_of_r2(double r2, double power, const dou
         return fma(r2, 5.0 / 3.0, 1.0 + a) * exp_neg_fast(a, tab);
     }
     if (KERN == 4) return cos(r);                                // Cosine
-    return exp(-power * log1p(0.5 * r2));                        // RatQuad
+    // RatQuad (1 + r^2 / 2)^-power = exp(-power ln u), power > 0; (r2 - r2) carries a NaN design through
+    return exp_neg_fast(fma(power, log_ge1_tab(fma(0.5, r2, 1.0), tab + kExpTabSize), r2 - r2), tab);
 }
 
 
@@ -129,7 +161,7 @@ struct EvalSmem {
     static constexpr int kRed = (RG > 1) ? kBlk * NCB : 0;
     static constexpr int kStage = kRec + kG;                     // one staging buffer
     static constexpr int kMain = kStage * (DB ? 2 : 1);
-    static constexpr int kDoubles = (kMain > kRed ? kMain : kRed) + kExpTabSize;
+    static constexpr int kDoubles = (kMain > kRed ? kMain : kRed) + kKernTabSize;
 };
 
 template <int KERN, int NXB, int NCB, int CPT, int RG, int MODE, bool ONE_RHS>
@@ -163,7 +195,7 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? GP
     double* sRec = smem;
     double* sG = smem + SM::kRec;                                // DB: buffer b lives at smem + b * SM::kStage
     double* sRed = smem;                                         // reused after the main loop
-    double* sTab = smem + (SM::kDoubles - kExpTabSize);
+    double* sTab = smem + (SM::kDoubles - kKernTabSize);
 
     const Item it = items[blockIdx.x];
     const GpView& g = gps[it.gp];
@@ -174,8 +206,7 @@ __global__ void __launch_bounds__(RG * (kBlk / CPT), (NCB <= 8) ? (CPT == 4 ? GP
     const int rg = tid / TPG, s = tid % TPG;
     const int n_pad = g.n_pad, nx = g.nx;
     const double power = g.power_x;
-    if (KERN <= 3)                                               // kernels evaluated with exp_neg_fast
-        for (int k = tid; k < kExpTabSize; k += kEvalThreads) sTab[k] = kExp2Tab[k];
+    load_kernel_tables<KERN>(sTab, tid, kEvalThreads);           // kernels evaluated with exp_neg_fast / log_ge1_tab
 
     double xs[CPT][NXB], cx[CPT];
 #pragma unroll

@@ -152,7 +152,7 @@ struct FusedSmem {
     double B[kFusedStages][kFusedBElems];
     unsigned long long full[kFusedStages];
     unsigned long long empty[kFusedStages];
-    double tab[kExpTabSize];
+    double tab[kKernTabSize];
 };
 
 __device__ __forceinline__ void fused_issue(FusedStream& ps, FusedSmem& sm) {
@@ -191,8 +191,7 @@ __global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) fused_kernel(c
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (KERN <= 3)
-        for (int k = threadIdx.x; k < kExpTabSize; k += kFusedThreads) fs.tab[k] = kExp2Tab[k];
+    load_kernel_tables<KERN>(fs.tab, threadIdx.x, kFusedThreads);
     __syncthreads();
 
     int stage = 0;

@@ -44,7 +44,7 @@ struct FcSmem {
     unsigned long long empty[kFcStages];
     unsigned long long ready[2];
     unsigned long long pfree[2];
-    double tab[kExpTabSize];
+    double tab[kKernTabSize];
     double rec[kFcRows * FcRec<NXB, NCB>::RS > kBlk * NCB ? kFcRows * FcRec<NXB, NCB>::RS : kBlk * NCB];
 };
 
@@ -251,8 +251,7 @@ __global__ void __launch_bounds__(kFcThreads, 1) fusedc_kernel(const FusedArgs a
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (KERN <= 3)
-        for (int k = threadIdx.x; k < kExpTabSize; k += kFcThreads) sm.tab[k] = kExp2Tab[k];
+    load_kernel_tables<KERN>(sm.tab, threadIdx.x, kFcThreads);
     __syncthreads();                                       // the only CTA-wide barrier
     double* priv = args.priv + (size_t)blockIdx.x * 2 * args.priv_stride;
 
